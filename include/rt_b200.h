@@ -1,0 +1,160 @@
+/*
+ * rt_b200.h -- C ABI of librt_b200.so: the B200 (sm_100a) implementation of the trace! -> segmentize!
+ * hot path of RayTracing.jl v0.2.3.
+ *
+ * The reference has no FFI of its own: its boundary is the Julia public API.  Each entry
+ * point below names the reference function whose work it replaces (file:line relative to the reference
+ * root); INTEGRATION.md shows the Julia `ccall` glue a maintainer adds on top.  Plain pointers and sizes
+ * only.  All functions return RT_OK (0) or a negative rt_status; rt_last_error(ctx) holds a message.
+ *
+ * Index conventions: mesh tables cross the ABI 1-BASED exactly as Gridap stores them (Table.data /
+ * Table.ptrs), track uids and element ids are 1-based as in the reference.  Host arrays are caller
+ * owned and only read/written during the call.  There is no CPU fallback: every call needs a CUDA device.
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rt_ctx rt_ctx;
+
+typedef enum rt_status {
+    RT_OK = 0,
+    RT_ERR_CUDA = -1,          /* CUDA runtime error (message has the detail) */
+    RT_ERR_ARG = -2,           /* invalid argument / call order */
+    RT_ERR_NO_EXIT = -4,       /* DomainError("could not found track exit point.")  trackgenerator.jl:219 */
+    RT_ERR_BC_MISMATCH = -5,   /* error("Boundaries do not match!")                 trackgenerator.jl:244 */
+    RT_ERR_NOT_ON_BOUNDARY = -6, /* error("Point do not lie in the boundary.")      boundary.jl:59 */
+    RT_ERR_NOT_TRACED = -7,    /* error("Segmentation is intended after tracing...") trackgenerator.jl:360 */
+    RT_ERR_TRACK = -8,         /* a track failed; see first_bad_uid / bad_status of rt_segmentize */
+    RT_ERR_NCCL = -9,
+    RT_ERR_NOMEM = -10
+} rt_status;
+
+/* per-track status written by rt_segmentize (the reference throws at the first such track) */
+enum {
+    RT_TRACK_OK = 0,
+    RT_TRACK_TRY_K = 1,   /* "Try increasing `k`..."                 src/track.jl:141 */
+    RT_TRACK_LENGTH = 2,  /* sum of segment lengths != track length  src/track.jl:171-175 */
+    RT_TRACK_RUNAWAY = 3, /* walk did not terminate (guard, no reference counterpart) */
+    RT_TRACK_UNDEF = 4    /* x_int1 undefined in intersections()     src/intersection.jl:81-95 */
+};
+
+/* boundary-condition codes = the reference's @enum BoundaryType (src/boundary.jl:12-16) */
+enum { RT_VACUUM = 0, RT_REFLECTIVE = 1, RT_PERIODIC = 2 };
+/* @enum DirectionType (src/track.jl:11-14) */
+enum { RT_FORWARD = 0, RT_BACKWARD = 1 };
+
+/* walk flags for rt_segmentize */
+enum {
+    RT_SEG_DEFAULT = 0,
+    RT_SEG_LITERAL = 1,     /* disable the adjacency fast path: every step re-locates like src/track.jl:122 */
+    RT_SEG_NO_VOLUMES = 2,  /* skip the fused fill_volumes accumulation */
+    RT_SEG_COUNT_ONLY = 4   /* count + scan only (no segment buffers are written) */
+};
+
+/* ---- context ------------------------------------------------------------------------------------- */
+int rt_create(rt_ctx **out, int device);
+void rt_destroy(rt_ctx *ctx);
+const char *rt_last_error(const rt_ctx *ctx);
+const char *rt_version(void);
+
+/* Pinned host memory helpers so callers can stage downloads at full PCIe speed. */
+int rt_host_alloc(void **ptr, size_t bytes);
+int rt_host_free(void *ptr);
+
+/* ---- mesh: replaces Mesh(model) (src/mesh.jl:24-31) + KDTree(grid) (src/mesh.jl:38-42) ---------------
+ * Uploads the flattened Gridap model and builds, on the device, the cell->neighbour table, per-cell and
+ * per-edge records (general_form of every edge, src/intersection.jl:11-18) and the uniform node grid
+ * that answers the exact nearest-node queries the reference asks its KD-tree (src/mesh.jl:107,123).
+ * xy = x0,y0,x1,y1,... ; cell_ptrs/cell_data = get_cell_node_ids(grid) ; node_cell_ptrs/node_cell_data =
+ * get_faces(topology, 0, 2) ; bb_min/bb_max = bounding_box(grid) (src/mesh.jl:53-69). Triangles only. */
+int rt_mesh_upload(rt_ctx *ctx, int32_t n_nodes, const double *xy, int32_t n_cells, const int32_t *cell_ptrs,
+                   const int32_t *cell_data, const int32_t *node_cell_ptrs, const int32_t *node_cell_data,
+                   const double bb_min[2], const double bb_max[2]);
+/* cell -> neighbour across edge (i, i%3+1) in the cell's stored node order, 1-based, 0 = boundary */
+int rt_mesh_neighbours(rt_ctx *ctx, int32_t *cell_nbr /* 3*n_cells */);
+
+/* ---- trace!: replaces trace!(t) (src/trackgenerator.jl:134-280) + next_tracks (:282-348) ------------
+ * One kernel over (phi, track) pairs.  The per-angle tables are computed by the CALLER with its own
+ * libm (Julia's when Julia calls) because sin/cos/tan/atan are not reproducible across libms:
+ * phi = tg.azimuthal_quadrature.phis, sin/cos/tan of it, dx_eff/dy_eff = the local dx/dy of trace!.
+ * bcs = top,bottom,right,left.  Only uids in [uid_begin, uid_end) (1-based, end exclusive) are generated
+ * on this context: that is the multi-GPU shard.  n_tracks_x/y are the constructor's counts
+ * (src/trackgenerator.jl:96-108). */
+int rt_trace(rt_ctx *ctx, int32_t n_azim_2, const int64_t *n_tracks_x, const int64_t *n_tracks_y,
+             const double *phi, const double *sin_phi, const double *cos_phi, const double *tan_phi,
+             const double *dx_eff, const double *dy_eff, const int32_t bcs[4], int64_t uid_begin,
+             int64_t uid_end);
+/* SoA over the shard's uids (index uid - uid_begin). Any pointer may be NULL.
+ * p,q: 2 doubles per track; abc: 3 per track (Track fields, src/track.jl:42-57). */
+int rt_tracks_download(rt_ctx *ctx, int64_t *azim_idx, int64_t *track_idx, double *p, double *q, double *phi,
+                       double *len, double *abc, int8_t *bc_fwd, int8_t *bc_bwd, int8_t *dir_fwd,
+                       int8_t *dir_bwd, int64_t *next_fwd_uid, int64_t *next_bwd_uid);
+/* Split [1, n_total] into n_parts contiguous uid ranges of equal total track length (bounds has
+ * n_parts+1 entries, bounds[0]=1, bounds[n_parts]=n_total+1). Same tables as rt_trace. */
+int rt_plan_shards(rt_ctx *ctx, int32_t n_azim_2, const int64_t *n_tracks_x, const int64_t *n_tracks_y,
+                   const double *phi, const double *tan_phi, const double *dx_eff, const double *dy_eff,
+                   int32_t n_parts, int64_t *bounds);
+
+/* ---- segmentize!: replaces segmentize!(t; k, rtol) (src/trackgenerator.jl:357-369), i.e. the loop over
+ * _segmentize_track! (src/track.jl:106-178) and fill_volumes (src/trackgenerator.jl:371-386) -----------
+ * count pass -> exclusive scan -> fill pass (+ fused per-element sum of delta_eff*len).
+ * tiny_step: TrackGenerator kwarg; k, rtol: segmentize! kwargs; max_iter: MAX_ITER (src/track.jl:104).
+ * delta_eff: tg.azimuthal_quadrature.deltas (n_azim_2 values) or NULL with RT_SEG_NO_VOLUMES.
+ * If the shard's segments exceed the context's segment capacity (rt_set_segment_capacity) the fill runs
+ * in uid batches over a recycled buffer and `cb` (may be NULL) is called once per batch.
+ * Returns RT_ERR_TRACK if any track failed (first_bad_uid, bad_status say which, like the reference's
+ * first thrown error); the other tracks are still segmentized. */
+typedef struct rt_batch {
+    int64_t uid_begin, uid_end;   /* tracks in this batch */
+    int64_t n_segments;           /* segments in this batch */
+    const int64_t *d_offsets;     /* DEVICE: offsets of the shard's tracks (n_shard+1), global to the shard */
+    int64_t offset_base;          /* subtract from d_offsets[uid-shard_begin] to index the arrays below */
+    const double *d_px, *d_py, *d_qx, *d_qy, *d_len; /* DEVICE SoA */
+    const int32_t *d_element;     /* DEVICE, 1-based element ids */
+    void *stream;                 /* cudaStream_t the batch was produced on */
+} rt_batch;
+typedef int (*rt_batch_cb)(const rt_batch *batch, void *user);
+
+int rt_set_segment_capacity(rt_ctx *ctx, int64_t max_segments_resident);
+int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rtol, int32_t max_iter,
+                  const double *delta_eff, uint32_t flags, rt_batch_cb cb, void *cb_user,
+                  int64_t *n_segments_total, int64_t *first_bad_uid, int32_t *bad_status);
+/* per-track segment counts / offsets / status of the shard after rt_segmentize (host copies) */
+int rt_segment_offsets(rt_ctx *ctx, int64_t *offsets /* n_shard+1 */, int32_t *status /* n_shard or NULL */);
+/* Segment(p, q, len, element) records (src/segment.jl:23-33) of the resident batch (the whole shard when
+ * it fitted), SoA, in uid order then walk order. Any pointer may be NULL. */
+int rt_segments_download(rt_ctx *ctx, double *px, double *py, double *qx, double *qy, double *len,
+                         int32_t *element);
+/* device-resident view of the resident batch for on-GPU consumers (transport sweeps) */
+int rt_segments_device(rt_ctx *ctx, rt_batch *view);
+
+/* ---- volumes: replaces the tail of fill_volumes (src/trackgenerator.jl:378-386) -----------------------
+ * volumes[e] = (sum over this context's segments of delta_eff[azim]*len) / n_azim_2, after an NCCL
+ * all-reduce across the communicator set up with rt_comm_init (skipped when there is none). */
+int rt_volumes(rt_ctx *ctx, double *volumes /* n_cells */);
+
+/* ---- multi-GPU: one context per process/GPU, tracks sharded by uid range, mesh replicated -----------
+ * rank 0 calls rt_comm_unique_id and ships the 128 bytes to the other ranks (MPI / torch.distributed /
+ * Julia Distributed); then every rank calls rt_comm_init. NCCL is resolved with dlopen at this point. */
+int rt_comm_unique_id(rt_ctx *ctx, char id[128]);
+int rt_comm_init(rt_ctx *ctx, int32_t n_ranks, int32_t rank, const char id[128]);
+
+/* ---- instrumentation -----------------------------------------------------------------------------
+ * stats[0..7] of the last rt_segmentize: kernel launches, fast transitions, slow (literal) iterations,
+ * nearest-node queries, knn queries, count-pass ms, fill-pass ms, scan+volumes ms. */
+int rt_stats(rt_ctx *ctx, double stats[8]);
+/* CUDA-event time (ms) of the last call's device work, by phase: 0 upload+prep, 1 trace, 2 count,
+ * 3 scan, 4 fill, 5 volumes(+allreduce) */
+int rt_phase_ms(rt_ctx *ctx, double ms[6]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_B200_H */

@@ -1,0 +1,466 @@
+"""Host-side mirror of RayTracing.jl's public API for the trace! -> segmentize! path.
+
+    tg = TrackGenerator(model, n_azim, delta, bcs=BoundaryConditions(...))   # src/trackgenerator.jl:80-125
+    trace_(tg)                                                                # trace!      (:134-280)
+    segmentize_(tg)                                                           # segmentize! (:357-369)
+    tg.tracks_by_uid[i].segments                                              # same layout as the reference
+
+Julia's ``!`` suffix becomes a trailing underscore.  Field and accessor names follow the reference
+(``phis`` = ϕs, ``deltas`` = δs, ``weights`` = ωₐ, ``ell`` = ℓ, ``tau`` = τ).  All geometry runs in the CUDA
+library behind the C ABI (include/rt_b200.h); this module only computes the <=128 per-angle libm values the
+ABI asks the caller for, and wraps device results in numpy arrays.  Indices are 1-based like the reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from enum import IntEnum
+
+import numpy as np
+
+from . import _lib
+from .mesh import Mesh, UnstructuredDiscreteModel
+
+RTOL_DEFAULT = math.sqrt(2.0 ** -52)  # Base.rtoldefault(Float64)
+MAX_ITER = 10_000  # src/track.jl:104
+
+
+class DomainError(ValueError):
+    """Julia's DomainError (src/azimuthal_quad.jl:22-25, src/trackgenerator.jl:219)."""
+
+
+class BoundaryType(IntEnum):  # src/boundary.jl:12-16
+    Vacuum = 0
+    Reflective = 1
+    Periodic = 2
+
+
+Vacuum, Reflective, Periodic = BoundaryType.Vacuum, BoundaryType.Reflective, BoundaryType.Periodic
+
+
+class DirectionType(IntEnum):  # src/track.jl:11-14
+    Forward = 0
+    Backward = 1
+
+
+Forward, Backward = DirectionType.Forward, DirectionType.Backward
+
+
+@dataclass(frozen=True)
+class BoundaryConditions:  # src/boundary.jl:38-46 (keyword constructor, all Vacuum by default)
+    top: BoundaryType = Vacuum
+    bottom: BoundaryType = Vacuum
+    right: BoundaryType = Vacuum
+    left: BoundaryType = Vacuum
+
+    def codes(self) -> np.ndarray:
+        return np.array([int(self.top), int(self.bottom), int(self.right), int(self.left)], dtype=np.int32)
+
+
+class AzimuthalQuadrature:  # src/azimuthal_quad.jl:8-34
+    def __init__(self, n_azim: int, delta: float):
+        if not n_azim > 0:
+            raise DomainError(f"{n_azim}: number of azimuthal angles must be positive.")
+        if n_azim % 4 != 0:
+            raise DomainError(f"{n_azim}: number of azimuthal angles must be a multiple of 4.")
+        if not delta > 0:
+            raise DomainError(f"{delta}: azimuthal spacing must be positive.")
+        self.n_azim = n_azim
+        self.delta = float(delta)
+        n2 = n_azim // 2
+        self.deltas = np.zeros(n2)
+        self.phis = np.zeros(n2)
+        self.weights = np.zeros(n2)
+
+
+def nazim(aq: AzimuthalQuadrature) -> int:
+    return aq.n_azim
+
+
+def nazim2(aq: AzimuthalQuadrature) -> int:
+    return aq.n_azim // 2
+
+
+def nazim4(aq: AzimuthalQuadrature) -> int:
+    return aq.n_azim // 4
+
+
+def init_weights_(aq: AzimuthalQuadrature) -> None:  # src/azimuthal_quad.jl:35-53
+    n2, n4 = nazim2(aq), nazim4(aq)
+    ph, w = aq.phis, aq.weights
+    for i in range(1, n4 + 1):
+        if i == 1:
+            v = ph[i] - ph[i - 1]
+        elif i == n4:
+            v = math.pi - ph[i - 1] - ph[i - 2]
+        else:
+            v = ph[i] - ph[i - 2]
+        v /= 4 * math.pi
+        w[i - 1] = v
+        w[n2 - i] = v
+
+
+class Segment:  # src/segment.jl:23-29
+    __slots__ = ("p", "q", "ell", "tau", "element")
+
+    def __init__(self, p, q, ell, element):
+        self.p, self.q, self.ell, self.tau, self.element = p, q, ell, [], element
+
+    def __repr__(self):
+        return f"Segment(p={self.p}, q={self.q}, ell={self.ell}, element={self.element})"
+
+
+class SegmentList:
+    """``track.segments``: a read-only sequence of Segment records backed by the SoA buffers."""
+
+    def __init__(self, tg, lo, hi):
+        self._tg, self._lo, self._hi = tg, lo, hi
+
+    def __len__(self):
+        return self._hi - self._lo
+
+    def __getitem__(self, i):
+        n = len(self)
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(n))]
+        if i < 0:
+            i += n
+        if not 0 <= i < n:
+            raise IndexError(i)
+        s, o = self._tg.segments, self._lo + i
+        return Segment(np.array([s["px"][o], s["py"][o]]), np.array([s["qx"][o], s["qy"][o]]), float(s["len"][o]),
+                       int(s["element"][o]))
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def arrays(self):
+        """SoA slices (px, py, qx, qy, len, element) of this track."""
+        return {k: v[self._lo:self._hi] for k, v in self._tg.segments.items()}
+
+
+class Track:  # src/track.jl:42-57 ; a view over the track SoA
+    def __init__(self, tg, idx):
+        self._tg, self._i = tg, idx
+
+    def _col(self, name):
+        return self._tg.track_data[name][self._i]
+
+    uid = property(lambda s: int(s._tg.uid_begin + s._i))
+    azim_idx = property(lambda s: int(s._col("azim_idx")))
+    track_idx = property(lambda s: int(s._col("track_idx")))
+    p = property(lambda s: s._col("p").copy())
+    q = property(lambda s: s._col("q").copy())
+    phi = property(lambda s: float(s._col("phi")))
+    ell = property(lambda s: float(s._col("len")))
+    ABC = property(lambda s: s._col("abc").copy())
+    next_track_fwd = property(lambda s: s._tg.tracks_by_uid[int(s._col("next_fwd"))])
+    next_track_bwd = property(lambda s: s._tg.tracks_by_uid[int(s._col("next_bwd"))])
+
+    @property
+    def segments(self):
+        off = self._tg.segment_offsets
+        base = self._tg._resident_base
+        return SegmentList(self._tg, int(off[self._i] - base), int(off[self._i + 1] - base))
+
+    def __repr__(self):
+        return f"Track(uid={self.uid}, azim_idx={self.azim_idx}, track_idx={self.track_idx}, p={self.p}, q={self.q})"
+
+
+def bc_fwd(track: Track) -> BoundaryType:  # src/track.jl:82
+    return BoundaryType(int(track._col("bc_fwd")))
+
+
+def bc_bwd(track: Track) -> BoundaryType:
+    return BoundaryType(int(track._col("bc_bwd")))
+
+
+def dir_next_track_fwd(track: Track) -> DirectionType:
+    return DirectionType(int(track._col("dir_fwd")))
+
+
+def dir_next_track_bwd(track: Track) -> DirectionType:
+    return DirectionType(int(track._col("dir_bwd")))
+
+
+def ell(x):  # RayTracing.ℓ (src/segment.jl:35)
+    return x.ell
+
+
+class _TracksByUid:
+    """``tg.tracks_by_uid[uid]`` with the reference's 1-based uid; only this rank's shard is resident."""
+
+    def __init__(self, tg):
+        self._tg = tg
+
+    def __len__(self):
+        return self._tg.n_total_tracks
+
+    def __getitem__(self, uid):
+        tg = self._tg
+        if not tg._traced:
+            raise RuntimeError("UndefRefError: access to undefined reference (call trace_ first)")
+        if isinstance(uid, slice):
+            return [self[u] for u in range(*uid.indices(len(self) + 1)) if u >= 1]
+        if not tg.uid_begin <= uid < tg.uid_end:
+            raise IndexError(f"uid {uid} outside this shard [{tg.uid_begin}, {tg.uid_end})")
+        return Track(tg, uid - tg.uid_begin)
+
+    def __iter__(self):
+        return (self[u] for u in range(self._tg.uid_begin, self._tg.uid_end))
+
+
+class _TracksByAngle:
+    """``tg.tracks[i][j]`` (1-based azimuthal index, then 1-based track index)."""
+
+    def __init__(self, tg, i=None):
+        self._tg, self._i = tg, i
+
+    def __getitem__(self, k):
+        tg = self._tg
+        if self._i is None:
+            if not 1 <= k <= nazim2(tg.azimuthal_quadrature):
+                raise IndexError(k)
+            return _TracksByAngle(tg, k)
+        if not 1 <= k <= tg.n_tracks[self._i - 1]:
+            raise IndexError(k)
+        return tg.tracks_by_uid[int(tg._base[self._i - 1] + k)]
+
+    def __len__(self):
+        tg = self._tg
+        return nazim2(tg.azimuthal_quadrature) if self._i is None else int(tg.n_tracks[self._i - 1])
+
+
+class TrackGenerator:
+    """TrackGenerator(model, n_azim, delta; bcs, tiny_step=1e-8, volume_correction=false)
+    (src/trackgenerator.jl:80-125).  Extra keywords select the GPU and the uid shard:
+    ``device`` (CUDA ordinal) and ``shard=(rank, n_ranks)`` -- tracks are split into ``n_ranks`` contiguous uid
+    ranges of equal total track length, the mesh is replicated."""
+
+    def __init__(self, model, n_azim: int, delta: float, bcs: BoundaryConditions | None = None, tiny_step: float = 1e-8,
+                 volume_correction: bool = False, device: int = 0, shard: tuple[int, int] = (0, 1)):
+        if isinstance(model, Mesh):
+            mesh = model
+        elif isinstance(model, UnstructuredDiscreteModel):
+            mesh = Mesh(model)
+        else:
+            raise TypeError("model must be an UnstructuredDiscreteModel")
+        self.mesh = mesh
+        self.bcs = bcs if bcs is not None else BoundaryConditions()
+        aq = AzimuthalQuadrature(n_azim, delta)
+        self.azimuthal_quadrature = aq
+        n2, n4 = nazim2(aq), nazim4(aq)
+        dx, dy = mesh.width, mesh.height
+        self.n_tracks_x = np.zeros(n2, dtype=np.int64)
+        self.n_tracks_y = np.zeros(n2, dtype=np.int64)
+        self.n_tracks = np.zeros(n2, dtype=np.int64)
+        for i in range(1, n4 + 1):  # src/trackgenerator.jl:96-108
+            phi = math.pi / n2 * (i - 1 / 2)
+            nx = int(math.floor(dx / delta * abs(math.sin(phi))) + 1)
+            ny = int(math.floor(dy / delta * abs(math.cos(phi))) + 1)
+            j = n2 - i + 1
+            self.n_tracks_x[i - 1] = self.n_tracks_x[j - 1] = nx
+            self.n_tracks_y[i - 1] = self.n_tracks_y[j - 1] = ny
+            self.n_tracks[i - 1] = self.n_tracks[j - 1] = nx + ny
+        self.n_total_tracks = int(self.n_tracks.sum())
+        self._base = np.concatenate([[0], np.cumsum(self.n_tracks)]).astype(np.int64)
+        self.tiny_step = float(tiny_step)
+        self.volume_correction = bool(volume_correction)
+        self.volumes = np.zeros(mesh.num_cells)
+        self.tracks = _TracksByAngle(self)
+        self.tracks_by_uid = _TracksByUid(self)
+        self.shard = (int(shard[0]), int(shard[1]))
+        self.uid_begin, self.uid_end = 1, self.n_total_tracks + 1
+        self._traced = False
+        self._segmented = False
+        self._track_data = None
+        self._segments = None
+        self._offsets = None
+        self._resident_base = 0
+        self._pinned = {}
+        self.n_segments = 0
+        # device context + mesh upload (Mesh(model), src/mesh.jl:24-31)
+        L = _lib.lib()
+        h = C.c_void_p()
+        rc = L.rt_create(C.byref(h), int(device))
+        if rc:
+            raise _lib.RTError(rc, f"rt_create(device={device}) failed: no usable CUDA device (there is no CPU fallback)")
+        self._ctx = h
+        m = mesh.model
+        _lib.check(h, L.rt_mesh_upload(h, m.num_nodes, m.node_coordinates.reshape(-1), m.num_cells, mesh.cell_nodes[0],
+                                       mesh.cell_nodes[1], mesh.node_cells[0], mesh.node_cells[1], mesh.bb_min, mesh.bb_max))
+
+    # ---- lazily fetched device results -------------------------------------------------------------
+    @property
+    def track_data(self):
+        if self._track_data is None:
+            if not self._traced:
+                raise RuntimeError("call trace_ first")
+            n = self.uid_end - self.uid_begin
+            t = dict(azim_idx=np.zeros(n, np.int64), track_idx=np.zeros(n, np.int64), p=np.zeros((n, 2)), q=np.zeros((n, 2)),
+                     phi=np.zeros(n), len=np.zeros(n), abc=np.zeros((n, 3)), bc_fwd=np.zeros(n, np.int8),
+                     bc_bwd=np.zeros(n, np.int8), dir_fwd=np.zeros(n, np.int8), dir_bwd=np.zeros(n, np.int8),
+                     next_fwd=np.zeros(n, np.int64), next_bwd=np.zeros(n, np.int64))
+            _lib.check(self._ctx, _lib.lib().rt_tracks_download(self._ctx, *[_lib.ptr(v) for v in t.values()]))
+            self._track_data = t
+        return self._track_data
+
+    @property
+    def segment_offsets(self):
+        if self._offsets is None:
+            if not self._segmented:
+                raise RuntimeError("call segmentize_ first")
+            n = self.uid_end - self.uid_begin
+            self._offsets = np.zeros(n + 1, np.int64)
+            self.segment_status = np.zeros(n, np.int32)
+            _lib.check(self._ctx, _lib.lib().rt_segment_offsets(self._ctx, _lib.ptr(self._offsets), _lib.ptr(self.segment_status)))
+        return self._offsets
+
+    @property
+    def segments(self):
+        """SoA dict px, py, qx, qy, len, element of the resident batch (the whole shard when it fitted)."""
+        if self._segments is None:
+            self.fetch_segments()
+        return self._segments
+
+    def fetch_segments(self, pinned: bool = True):
+        """Device -> host copy of the Segment records (into reusable pinned buffers by default)."""
+        if not self._segmented:
+            raise RuntimeError("call segmentize_ first")
+        L = _lib.lib()
+        view = _lib.rt_batch()
+        _lib.check(self._ctx, L.rt_segments_device(self._ctx, C.byref(view)))
+        n = int(view.n_segments)
+        self._resident_base = int(view.offset_base)
+        names = [("px", np.float64), ("py", np.float64), ("qx", np.float64), ("qy", np.float64), ("len", np.float64),
+                 ("element", np.int32)]
+        out = {}
+        for name, dt in names:
+            if pinned:
+                buf = self._pinned.get(name)
+                if buf is None or buf.array.shape[0] < n:
+                    if buf is not None:
+                        buf.free()
+                    buf = _lib.PinnedArray((max(n, 1),), dt)
+                    self._pinned[name] = buf
+                out[name] = buf.array[:n]
+            else:
+                out[name] = np.zeros(n, dt)
+        _lib.check(self._ctx, L.rt_segments_download(self._ctx, *[_lib.ptr(out[k]) for k, _ in names]))
+        self._segments = out
+        return out
+
+    def phase_ms(self):
+        ms = np.zeros(6)
+        _lib.lib().rt_phase_ms(self._ctx, ms)
+        return dict(zip(["upload", "trace", "count", "scan", "fill", "volumes"], ms.tolist()))
+
+    def stats(self):
+        s = np.zeros(8)
+        _lib.lib().rt_stats(self._ctx, s)
+        return dict(zip(["launches", "fast_transitions", "literal_iterations", "nn_queries", "knn_queries", "count_ms",
+                         "fill_ms", "scan_ms"], s.tolist()))
+
+    def neighbours(self):
+        nb = np.zeros(3 * self.mesh.num_cells, np.int32)
+        _lib.check(self._ctx, _lib.lib().rt_mesh_neighbours(self._ctx, nb))
+        return nb.reshape(-1, 3)
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            for b in self._pinned.values():
+                b.free()
+            self._pinned = {}
+            self._segments = None
+            _lib.lib().rt_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __repr__(self):  # src/trackgenerator.jl:52-63
+        aq = self.azimuthal_quadrature
+        return ("  Number of azimuthal angles in (0, π): %d\n  Azimuthal angles in (0, π): %s\n"
+                "  Effective azimuthal spacings: %s\n  Total tracks: %d\n  Correct volumes: %s" %
+                (nazim2(aq), np.round(np.degrees(aq.phis), 2), np.round(aq.deltas, 3), self.n_total_tracks,
+                 str(self.volume_correction).lower()))
+
+
+def _angle_tables(tg: TrackGenerator):
+    """Effective angles/spacings of trace! (src/trackgenerator.jl:150-166) with the host libm, plus the sin/cos/tan
+    tables the device needs (no device trigonometry, see include/rt_b200.h)."""
+    aq = tg.azimuthal_quadrature
+    n2, n4 = nazim2(aq), nazim4(aq)
+    dx, dy = tg.mesh.width, tg.mesh.height
+    dxe, dye = np.zeros(n2), np.zeros(n2)
+    for i in range(1, n4 + 1):
+        phi = math.atan((dy * float(tg.n_tracks_x[i - 1])) / (dx * float(tg.n_tracks_y[i - 1])))
+        aq.phis[i - 1] = phi
+        dxe[i - 1] = dx / float(tg.n_tracks_x[i - 1])
+        dye[i - 1] = dy / float(tg.n_tracks_y[i - 1])
+        aq.deltas[i - 1] = dxe[i - 1] * math.sin(phi)
+        j = n2 - i + 1
+        aq.phis[j - 1] = math.pi - phi
+        dxe[j - 1], dye[j - 1], aq.deltas[j - 1] = dxe[i - 1], dye[i - 1], aq.deltas[i - 1]
+    init_weights_(aq)
+    sin_t = np.array([math.sin(p) for p in aq.phis])
+    cos_t = np.array([math.cos(p) for p in aq.phis])
+    tan_t = np.array([math.tan(p) for p in aq.phis])
+    return sin_t, cos_t, tan_t, dxe, dye
+
+
+def trace_(tg: TrackGenerator) -> TrackGenerator:
+    """trace!(tg): effective quadrature on the host, then ONE kernel over (phi, track) pairs."""
+    L = _lib.lib()
+    sin_t, cos_t, tan_t, dxe, dye = _angle_tables(tg)
+    aq = tg.azimuthal_quadrature
+    n2 = nazim2(aq)
+    rank, n_ranks = tg.shard
+    if n_ranks > 1:
+        from .distributed import plan_shards
+
+        bounds = plan_shards(tg, n_ranks)  # host planner (rt_plan_shards is the same split computed on the device)
+        tg.shard_bounds = bounds
+        tg.uid_begin, tg.uid_end = int(bounds[rank]), int(bounds[rank + 1])
+    else:
+        tg.uid_begin, tg.uid_end = 1, tg.n_total_tracks + 1
+    tg._traced = False
+    tg._segmented = False
+    tg._track_data = tg._segments = tg._offsets = None
+    rc = L.rt_trace(tg._ctx, n2, tg.n_tracks_x, tg.n_tracks_y, aq.phis, sin_t, cos_t, tan_t, dxe, dye, tg.bcs.codes(),
+                    tg.uid_begin, tg.uid_end)
+    if rc == -4:
+        raise DomainError("could not found track exit point.")
+    _lib.check(tg._ctx, rc)
+    tg._traced = True
+    return tg
+
+
+def segmentize_(tg: TrackGenerator, k: int = 5, rtol: float = RTOL_DEFAULT, flags: int = 0, max_iter: int = MAX_ITER,
+                check: bool = True) -> TrackGenerator:
+    """segmentize!(tg; k, rtol): count pass -> scan -> fill pass (+ fused fill_volumes) on the device."""
+    L = _lib.lib()
+    if not tg._traced:
+        raise RuntimeError("Segmentation is intended after tracing. Please, call `trace!` first!")
+    tg._segmented = False
+    tg._segments = tg._offsets = None
+    nseg, bad_uid, bad_status = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+    delta = tg.azimuthal_quadrature.deltas
+    rc = L.rt_segmentize(tg._ctx, tg.tiny_step, int(k), float(rtol), int(max_iter), _lib.ptr(delta), int(flags), None, None,
+                         C.byref(nseg), C.byref(bad_uid), C.byref(bad_status))
+    tg.n_segments = int(nseg.value)
+    tg.first_bad_uid, tg.bad_status = int(bad_uid.value), int(bad_status.value)
+    if rc == -8:
+        tg._segmented = True
+        if check:
+            _lib.check(tg._ctx, rc)
+    else:
+        _lib.check(tg._ctx, rc)
+        tg._segmented = True
+    if not (flags & _lib.RT_SEG_NO_VOLUMES):
+        _lib.check(tg._ctx, L.rt_volumes(tg._ctx, _lib.ptr(tg.volumes)))
+    return tg

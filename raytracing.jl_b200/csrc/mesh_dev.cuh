@@ -1,0 +1,362 @@
+// mesh_dev.cuh -- device-resident flattened mesh, its preparation kernels, and the literal point
+// location of the reference (find_element / point_in_triangle / inboundary, src/mesh.jl:91-176) with the
+// KD-tree of NearestNeighbors.jl replaced by an exact uniform-grid nearest-node search.
+#pragma once
+#include "geom.cuh"
+
+namespace rt {
+
+// 64-byte per-cell record read once per fast transition (two 32 B sectors, no dependent gathers).
+struct __align__(32) CellRec {
+    double vx[3];
+    double vy[3];
+    int nbr[3];   // 0-based cell across edge k = (k, (k+1)%3); -1 on the boundary
+    float clear;  // required perpendicular clearance of the track from this cell's vertices; +inf = always literal
+};
+static_assert(sizeof(CellRec) == 64, "CellRec must be 64 bytes");
+
+// 32-byte per-(cell, edge) record: general_form(P_k, P_k+1) (src/intersection.jl:57) and |P_k - P_k+1|.
+struct __align__(32) EdgeRec {
+    double a, b, c, len;
+};
+
+struct DevMesh {
+    int n_nodes, n_cells;
+    const double2 *xy;      // node coordinates
+    const int *cell_nodes;  // 3*n_cells, 0-based, stored (Gridap) order
+    const int *nc_ptrs;     // node -> cells CSR, 0-based, caller's order (src/mesh.jl:27)
+    const int *nc_data;
+    const CellRec *cells;
+    const EdgeRec *edges;  // [3*cell + k]
+    // uniform node grid
+    int gx, gy;
+    double g0x, g0y, gh, ginv;
+    const int *grid_ptrs;   // gx*gy + 1
+    const int *grid_nodes;  // node ids binned
+    double bbmin[2], bbmax[2];
+};
+
+// ------------------------------------------------------------------------------------------------
+// preparation kernels (run once per rt_mesh_upload)
+// ------------------------------------------------------------------------------------------------
+
+__global__ void k_to_zero_based(const int32_t *in, int *out, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] - 1;
+}
+
+// one thread per (cell, edge): the neighbour is the other cell around node a that also contains node b
+__global__ void k_neighbours(int n_cells, const int *cell_nodes, const int *nc_ptrs, const int *nc_data, int *nbr) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= 3 * (int64_t)n_cells) return;
+    int c = (int)(t / 3), k = (int)(t % 3);
+    int a = cell_nodes[3 * c + k], b = cell_nodes[3 * c + (k + 1) % 3];
+    int found = -1;
+    for (int q = nc_ptrs[a]; q < nc_ptrs[a + 1]; ++q) {
+        int c2 = nc_data[q];
+        if (c2 == c) continue;
+        const int *n2 = &cell_nodes[3 * c2];
+        if (n2[0] == b || n2[1] == b || n2[2] == b) {
+            found = c2;
+            break;
+        }
+    }
+    nbr[t] = found;
+}
+
+struct MeshScalars {
+    double lmax;  // longest edge
+    double smax;  // largest |coordinate|
+};
+
+__device__ __forceinline__ void atomic_max_double(double *addr, double v) {
+    // values are non-negative: ordering of the bit patterns equals ordering of the doubles
+    atomicMax((unsigned long long *)addr, (unsigned long long)__double_as_longlong(v));
+}
+
+// per cell: vertex coordinates, neighbours, edge records, geometric quality numbers
+// qual[c] = (1 + 8*eps*(S/hmin)^2/rtol) / sigma, sigma = min sine of the interior angles; bdist[c] = min distance of
+// the cell's vertices from the bounding-box lines.  (clear is finalised per segmentize call, it depends on tiny_step.)
+__global__ void k_cell_records(DevMesh m, const int *nbr, CellRec *cells, EdgeRec *edges, float *qual, float *bdist,
+                               MeshScalars *sc) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m.n_cells) return;
+    P2 v[3];
+    for (int k = 0; k < 3; ++k) {
+        double2 p = m.xy[m.cell_nodes[3 * c + k]];
+        v[k].x = p.x;
+        v[k].y = p.y;
+    }
+    CellRec r;
+    double lmax = 0.0, smax = 0.0, bd = INFINITY;
+    double len[3];
+    for (int k = 0; k < 3; ++k) {
+        int j = (k + 1) % 3;
+        r.vx[k] = v[k].x;
+        r.vy[k] = v[k].y;
+        r.nbr[k] = nbr[3 * c + k];
+        Line l = general_form(v[k], v[j]);
+        EdgeRec e;
+        e.a = l.a;
+        e.b = l.b;
+        e.c = l.c;
+        e.len = norm2(v[k].x - v[j].x, v[k].y - v[j].y);
+        edges[3 * c + k] = e;
+        len[k] = e.len;
+        lmax = fmax(lmax, e.len);
+        smax = fmax(smax, fmax(fabs(v[k].x), fabs(v[k].y)));
+        bd = fmin(bd, fmin(fmin(fabs(v[k].x - m.bbmin[0]), fabs(v[k].x - m.bbmax[0])),
+                           fmin(fabs(v[k].y - m.bbmin[1]), fabs(v[k].y - m.bbmax[1]))));
+    }
+    double area2 = fabs((v[1].x - v[0].x) * (v[2].y - v[0].y) - (v[2].x - v[0].x) * (v[1].y - v[0].y));
+    // sine of the angle at vertex k = 2*Area / (product of the two edges meeting there)
+    double s0 = area2 / (len[0] * len[2]), s1 = area2 / (len[0] * len[1]), s2 = area2 / (len[1] * len[2]);
+    double sigma = fmin(s0, fmin(s1, s2));
+    double hmin = area2 / lmax;
+    r.clear = INFINITY;
+    cells[c] = r;
+    qual[c] = (sigma > 0.0 && hmin > 0.0) ? (float)(1.0 / sigma) : INFINITY;
+    bdist[c] = (float)bd;
+    // hmin feeds the lambda rounding-error term; stash via a second pass using smax (global), see k_finalize_clear
+    atomic_max_double(&sc->lmax, lmax);
+    atomic_max_double(&sc->smax, smax);
+}
+
+// clear[c] for one (tiny_step) value; see DESIGN.md "fast-path equivalence" for the derivation.
+//   reach R = (8*rtol + 64*eps*(S/hmin_c)^2) * Lmax      (how far outside a cell its tolerant test can pass)
+//   clear_c = 16 * (R + tiny) / sigma_c                     (+inf for cells touching the bounding box band)
+__global__ void k_finalize_clear(DevMesh m, CellRec *cells, const float *qual, const float *bdist, const MeshScalars *sc,
+                                 double tiny) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m.n_cells) return;
+    const CellRec &r = cells[c];
+    double lmax = 0.0;
+    for (int k = 0; k < 3; ++k) lmax = fmax(lmax, m.edges[3 * c + k].len);
+    double area2 = fabs((r.vx[1] - r.vx[0]) * (r.vy[2] - r.vy[0]) - (r.vx[2] - r.vx[0]) * (r.vy[1] - r.vy[0]));
+    double hmin = area2 / lmax;
+    double ratio = sc->smax / hmin;
+    double reach = (8.0 * kRtol + 64.0 * 2.220446049250313e-16 * ratio * ratio) * sc->lmax;
+    double clear = 16.0 * (reach + tiny) * (double)qual[c] * 1.001;
+    bool boundary = !((double)bdist[c] > 8.0 * tiny + 1e-12 * sc->smax);
+    float cf = (float)clear;
+    if (!(cf >= clear)) cf = nextafterf(cf, INFINITY);
+    if (boundary || !isfinite(clear) || !(hmin > 0.0)) cf = INFINITY;
+    cells[c].clear = cf;
+}
+
+// ---- uniform node grid -------------------------------------------------------------------------
+__device__ __forceinline__ int grid_bin(const DevMesh &m, double x, double y) {
+    int bx = (int)floor((x - m.g0x) * m.ginv);
+    int by = (int)floor((y - m.g0y) * m.ginv);
+    bx = min(max(bx, 0), m.gx - 1);
+    by = min(max(by, 0), m.gy - 1);
+    return by * m.gx + bx;
+}
+
+__global__ void k_grid_count(DevMesh m, int *counts) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m.n_nodes) return;
+    double2 p = m.xy[i];
+    atomicAdd(&counts[grid_bin(m, p.x, p.y)], 1);
+}
+
+__global__ void k_grid_fill(DevMesh m, const int *ptrs, int *cursor, int *nodes) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m.n_nodes) return;
+    double2 p = m.xy[i];
+    int b = grid_bin(m, p.x, p.y);
+    int pos = atomicAdd(&cursor[b], 1);
+    nodes[ptrs[b] + pos] = i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// literal point location
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kMaxK = 8;
+
+struct KBest {
+    double d2[kMaxK];
+    int id[kMaxK];
+    int n, k;
+};
+
+__device__ __forceinline__ bool cand_less(double d2a, int ida, double d2b, int idb) {
+    return d2a < d2b || (d2a == d2b && ida < idb);
+}
+
+__device__ __forceinline__ void kbest_insert(KBest &s, double d2, int id) {
+    if (s.n == s.k && !cand_less(d2, id, s.d2[s.k - 1], s.id[s.k - 1])) return;
+    int pos = s.n < s.k ? s.n : s.k - 1;
+    while (pos > 0 && cand_less(d2, id, s.d2[pos - 1], s.id[pos - 1])) {
+        s.d2[pos] = s.d2[pos - 1];
+        s.id[pos] = s.id[pos - 1];
+        --pos;
+    }
+    s.d2[pos] = d2;
+    s.id[pos] = id;
+    if (s.n < s.k) s.n++;
+}
+
+// Exact k nearest nodes of (x, y) (ties: lowest node id), skipping node `skip` -- what the reference asks of
+// nn(kdtree, x) (src/mesh.jl:107) and knn(kdtree, x, k, true, skip) (src/mesh.jl:123). Ring search: after ring r every
+// unvisited node is farther than the distance to the border of the visited block.
+__device__ __noinline__ void knn_query(const DevMesh &m, double x, double y, int skip, KBest &s) {
+    s.n = 0;
+    int bx = (int)floor((x - m.g0x) * m.ginv);
+    int by = (int)floor((y - m.g0y) * m.ginv);
+    bx = min(max(bx, 0), m.gx - 1);
+    by = min(max(by, 0), m.gy - 1);
+    const double slack = 1e-7 * m.gh;
+    int rmax = max(m.gx, m.gy);
+    for (int r = 0; r <= rmax; ++r) {
+        int x0 = bx - r, x1 = bx + r, y0 = by - r, y1 = by + r;
+        for (int iy = max(y0, 0); iy <= min(y1, m.gy - 1); ++iy) {
+            bool edge_row = (iy == y0 || iy == y1);
+            int step = edge_row ? 1 : (x1 - x0);
+            if (step == 0) step = 1;
+            for (int ix = x0; ix <= x1; ix += step) {
+                if (ix < 0 || ix >= m.gx) continue;
+                int b = iy * m.gx + ix;
+                for (int q = m.grid_ptrs[b]; q < m.grid_ptrs[b + 1]; ++q) {
+                    int id = m.grid_nodes[q];
+                    if (id == skip) continue;
+                    double2 p = m.xy[id];
+                    double dx = x - p.x, dy = y - p.y;
+                    kbest_insert(s, dx * dx + dy * dy, id);
+                }
+            }
+        }
+        bool covers = (x0 <= 0 && y0 <= 0 && x1 >= m.gx - 1 && y1 >= m.gy - 1);
+        if (covers) break;
+        if (s.n == s.k) {
+            double bound = INFINITY;
+            if (x0 > 0) bound = fmin(bound, x - (m.g0x + x0 * m.gh));
+            if (x1 < m.gx - 1) bound = fmin(bound, (m.g0x + (x1 + 1) * m.gh) - x);
+            if (y0 > 0) bound = fmin(bound, y - (m.g0y + y0 * m.gh));
+            if (y1 < m.gy - 1) bound = fmin(bound, (m.g0y + (y1 + 1) * m.gh) - y);
+            bound -= slack;
+            if (bound > 0.0 && s.d2[s.k - 1] < bound * bound) break;
+        }
+    }
+}
+
+// point_in_triangle  src/mesh.jl:158-176 ; lambda = R \ r by the StaticArrays 3x3 closed form
+__device__ __forceinline__ bool point_in_triangle(const DevMesh &m, int cell, double x, double y) {
+    const int *nid = &m.cell_nodes[3 * cell];
+    double2 a = m.xy[nid[0]], b = m.xy[nid[1]], c = m.xy[nid[2]];
+    double x1 = a.x, y1 = a.y, x2 = b.x, y2 = b.y, x3 = c.x, y3 = c.y;
+    double d = x1 * (y2 - y3) + y1 * (x3 - x2) + (x2 * y3 - y2 * x3);
+    double l1 = ((y2 - y3) * x + (x3 - x2) * y + (x2 * y3 - x3 * y2)) / d;
+    double l2 = ((y3 - y1) * x + (x1 - x3) * y + (x3 * y1 - x1 * y3)) / d;
+    double l3 = ((y1 - y2) * x + (x2 - x1) * y + (x1 * y2 - x2 * y1)) / d;
+    const double lo = 0.0 - kRtol, hi = 1.0 + kRtol;
+    return (lo <= l1 && l1 <= hi) && (lo <= l2 && l2 <= hi) && (lo <= l3 && l3 <= hi);
+}
+
+__device__ __forceinline__ int scan_node_cells(const DevMesh &m, int node, double x, double y) {
+    for (int q = m.nc_ptrs[node]; q < m.nc_ptrs[node + 1]; ++q) {
+        int cell = m.nc_data[q];
+        if (point_in_triangle(m, cell, x, y)) return cell;
+    }
+    return -1;
+}
+
+// find_element(mesh, x, k)  src/mesh.jl:103-146 ; returns 0-based cell or -1
+__device__ __noinline__ int find_element(const DevMesh &m, double x, double y, int k, unsigned long long *nq) {
+    KBest s;
+    s.k = 1;
+    knn_query(m, x, y, -1, s);
+    if (nq) nq[0]++;
+    int nn = s.id[0];
+    int c = scan_node_cells(m, nn, x, y);
+    if (c >= 0) return c;
+    s.k = min(k, kMaxK);
+    knn_query(m, x, y, nn, s);
+    if (nq) nq[1]++;
+    for (int i = 0; i < s.n; ++i) {
+        c = scan_node_cells(m, s.id[i], x, y);
+        if (c >= 0) return c;
+    }
+    return -1;
+}
+
+// inboundary(mesh, x, atol)  src/mesh.jl:91-95
+__device__ __forceinline__ bool inboundary(const DevMesh &m, double x, double y, double atol) {
+    double rtol = atol > 0.0 ? 0.0 : kRtol;
+    return isapprox(x, m.bbmax[0], atol, rtol) || isapprox(x, m.bbmin[0], atol, rtol) ||
+           isapprox(y, m.bbmax[1], atol, rtol) || isapprox(y, m.bbmin[1], atol, rtol);
+}
+
+// intersections(mesh, cell, track)  src/intersection.jl:34-119 (triangles: 3 edges, at most 3 hits).
+// Returns 0, or 4 (RT_TRACK_UNDEF) when the 3-hit selection never assigns x_int1. e_p/e_q: local edges of p and q.
+__device__ __noinline__ int intersections(const DevMesh &m, int cell, const Line &trk, bool phi_lt_half_pi, P2 &p, P2 &q,
+                                          int &e_p, int &e_q) {
+    const CellRec &r = m.cells[cell];
+    P2 ip[3];
+    int ie[3];
+    int n_int = 0;
+    bool parallel_found = false;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        int j = (i == 2) ? 0 : i + 1;
+        const EdgeRec e = m.edges[3 * cell + i];
+        Line L;
+        L.a = e.a;
+        L.b = e.b;
+        L.c = e.c;
+        P2 X;
+        bool par = intersection(trk, L, X);
+        if (par) {
+            parallel_found = true;
+            continue;
+        }
+        P2 p1{r.vx[i], r.vy[i]}, p2{r.vx[j], r.vy[j]};
+        if (!point_in_segment(p1, p2, e.len, X)) continue;
+        ip[n_int] = X;
+        ie[n_int] = i;
+        n_int++;
+    }
+    e_p = e_q = -1;
+    if (n_int == 3) {
+        double l = 0.0;
+        int s1 = -1, s2 = -1;
+        // for i in 2:n, j in i:n: x1 = pts[i-1], x2 = pts[j]  -> pairs (1,2) (1,3) (2,3)
+        const int pa[3] = {0, 0, 1}, pb[3] = {1, 2, 2};
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            double li = norm2(ip[pa[t]].x - ip[pb[t]].x, ip[pa[t]].y - ip[pb[t]].y);
+            if (li > l) {
+                s1 = pa[t];
+                s2 = pb[t];
+                l = li;
+            }
+        }
+        if (s1 < 0) return 4;
+        bool first = order_first(phi_lt_half_pi, ip[s1], ip[s2]);
+        p = first ? ip[s1] : ip[s2];
+        q = first ? ip[s2] : ip[s1];
+        e_p = first ? ie[s1] : ie[s2];
+        e_q = first ? ie[s2] : ie[s1];
+        return 0;
+    }
+    if (n_int == 2) {
+        if (!parallel_found && isapprox_pt(ip[0], ip[1])) {
+            p = ip[0];
+            q = ip[1];
+            e_p = ie[0];
+            e_q = ie[1];
+            return 0;
+        }
+        bool first = order_first(phi_lt_half_pi, ip[0], ip[1]);
+        p = first ? ip[0] : ip[1];
+        q = first ? ip[1] : ip[0];
+        e_p = first ? ie[0] : ie[1];
+        e_q = first ? ie[1] : ie[0];
+        return 0;
+    }
+    p.x = p.y = q.x = q.y = 0.0;
+    return 0;
+}
+
+}  // namespace rt

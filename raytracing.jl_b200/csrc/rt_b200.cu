@@ -1,0 +1,876 @@
+// rt_b200.cu -- the C ABI of include/rt_b200.h on top of the sm_100a kernels (mesh_dev.cuh, trace.cuh,
+// walk.cuh, scan.cuh).  Build (see __graft_entry__.build):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+// -fmad=false is REQUIRED for bit-parity with the reference's IEEE arithmetic (Julia never fuses a*b+c).
+#include "../../include/rt_b200.h"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "scan.cuh"
+#include "trace.cuh"
+
+using namespace rt;
+
+// ---- minimal NCCL surface, resolved with dlopen so the library has no link-time dependency ------------
+typedef struct ncclComm *ncclComm_t;
+typedef struct {
+    char internal[128];
+} ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat64 = 8, ncclSum = 0 };
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+struct rt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+
+    // mesh
+    bool has_mesh = false;
+    DevMesh m{};
+    DevBuf b_xy, b_cell_nodes, b_nc_ptrs, b_nc_data, b_nbr, b_cells, b_edges, b_qual, b_bdist, b_sc, b_grid_ptrs,
+        b_grid_nodes;
+    double clear_tiny = -1.0;
+    double smax = 0.0, lmax = 0.0;
+
+    // per-angle tables
+    int n2 = 0;
+    DevBuf b_ang_d, b_ang_i;  // doubles: phi,sin,cos,tan,dxe,dye,delta ; int64: nx,ny,base(n2+1)
+    std::vector<long long> h_base;
+    std::vector<double> h_phi;
+    bool has_delta = false;
+
+    // tracks of the shard
+    bool traced = false;
+    long long uid_begin = 1, n_shard = 0;
+    TrackSoA t{};
+    DevBuf b_trk_d, b_trk_i, b_trk_l, b_trk_c;
+    DevBuf b_err;
+
+    // segmentation
+    bool segmented = false;
+    DevBuf b_count, b_status, b_offsets, b_tile, b_vol, b_voln, b_counters, b_bad;
+    long long total_segments = 0;
+    long long cap_cfg = 0;  // user limit on resident segments (0 = as many as fit)
+    long long cap = 0;      // allocated
+    DevBuf b_seg_d, b_seg_e;
+    double *s_px = nullptr, *s_py = nullptr, *s_qx = nullptr, *s_qy = nullptr, *s_len = nullptr;
+    int *s_elem = nullptr;
+    long long res_trk_begin = 0, res_trk_end = 0, res_off_base = 0, res_nseg = 0;  // resident batch (shard-local)
+    bool vol_valid = false;
+
+    double phase_ms[6] = {0, 0, 0, 0, 0, 0};
+    double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+    // NCCL
+    NcclApi nccl;
+    ncclComm_t comm = nullptr;
+    int n_ranks = 1, rank = 0;
+};
+
+static int fail(rt_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return fail(ctx, RT_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,              \
+                        cudaGetErrorString(e_));                                                              \
+    } while (0)
+
+static cudaError_t ensure(DevBuf &b, size_t bytes) {
+    if (bytes <= b.bytes && b.p) return cudaSuccess;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+    cudaError_t e = cudaMalloc(&b.p, bytes ? bytes : 1);
+    if (e == cudaSuccess) b.bytes = bytes;
+    return e;
+}
+static void release(DevBuf &b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+}
+
+static inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+template <typename Tin, typename Tout>
+static cudaError_t exclusive_scan(rt_ctx *ctx, const Tin *in, Tout *out, long long n) {
+    long long n_tiles = (n + kScanTile - 1) / kScanTile;
+    cudaError_t e = ensure(ctx->b_tile, sizeof(Tout) * (size_t)n_tiles);
+    if (e != cudaSuccess) return e;
+    Tout *tiles = (Tout *)ctx->b_tile.p;
+    k_scan_tile_sums<Tin, Tout><<<(unsigned)n_tiles, kScanThreads, 0, ctx->stream>>>(in, tiles, n);
+    k_scan_tile_offsets<Tout><<<1, kScanThreads, 0, ctx->stream>>>(tiles, n_tiles);
+    k_scan_apply<Tin, Tout><<<(unsigned)n_tiles, kScanThreads, 0, ctx->stream>>>(in, out, tiles, n);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------
+extern "C" const char *rt_version(void) { return "rt_b200 0.1 (sm_100a, fp64, fmad=false)"; }
+
+extern "C" int rt_create(rt_ctx **out, int device) {
+    if (!out) return RT_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) return RT_ERR_CUDA;  // no CPU fallback
+    rt_ctx *ctx = new rt_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev[0]) != cudaSuccess || cudaEventCreate(&ctx->ev[1]) != cudaSuccess) {
+        delete ctx;
+        return RT_ERR_CUDA;
+    }
+    *out = ctx;
+    return RT_OK;
+}
+
+extern "C" void rt_destroy(rt_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
+    DevBuf *all[] = {&ctx->b_xy,      &ctx->b_cell_nodes, &ctx->b_nc_ptrs,  &ctx->b_nc_data, &ctx->b_nbr,     &ctx->b_cells,
+                     &ctx->b_edges,   &ctx->b_qual,       &ctx->b_bdist,    &ctx->b_sc,      &ctx->b_grid_ptrs, &ctx->b_grid_nodes,
+                     &ctx->b_ang_d,   &ctx->b_ang_i,      &ctx->b_trk_d,    &ctx->b_trk_i,   &ctx->b_trk_l,   &ctx->b_trk_c,
+                     &ctx->b_err,     &ctx->b_count,      &ctx->b_status,   &ctx->b_offsets, &ctx->b_tile,    &ctx->b_vol,
+                     &ctx->b_voln,    &ctx->b_counters,   &ctx->b_bad,      &ctx->b_seg_d,   &ctx->b_seg_e};
+    for (DevBuf *b : all) release(*b);
+    if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
+    if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char *rt_last_error(const rt_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int rt_host_alloc(void **ptr, size_t bytes) {
+    return cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? RT_OK : RT_ERR_NOMEM;
+}
+extern "C" int rt_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? RT_OK : RT_ERR_CUDA; }
+
+static void tic(rt_ctx *ctx) { cudaEventRecord(ctx->ev[0], ctx->stream); }
+static double toc(rt_ctx *ctx) {
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    cudaEventSynchronize(ctx->ev[1]);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    return (double)ms;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// mesh
+// ------------------------------------------------------------------------------------------------------
+extern "C" int rt_mesh_upload(rt_ctx *ctx, int32_t n_nodes, const double *xy, int32_t n_cells, const int32_t *cell_ptrs,
+                              const int32_t *cell_data, const int32_t *node_cell_ptrs, const int32_t *node_cell_data,
+                              const double bb_min[2], const double bb_max[2]) {
+    if (!ctx) return RT_ERR_ARG;
+    if (n_nodes < 3 || n_cells < 1 || !xy || !cell_ptrs || !cell_data || !node_cell_ptrs || !node_cell_data)
+        return fail(ctx, RT_ERR_ARG, "rt_mesh_upload: null or empty mesh arrays");
+    for (int32_t c = 0; c < n_cells; ++c)
+        if (cell_ptrs[c + 1] - cell_ptrs[c] != 3)
+            return fail(ctx, RT_ERR_ARG, "rt_mesh_upload: cell %d is not a triangle (reference src/mesh.jl:149-150)", c + 1);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    tic(ctx);
+    size_t n_nc = (size_t)(node_cell_ptrs[n_nodes] - 1);
+    CK(ensure(ctx->b_xy, sizeof(double2) * (size_t)n_nodes));
+    CK(ensure(ctx->b_cell_nodes, sizeof(int) * 3 * (size_t)n_cells));
+    CK(ensure(ctx->b_nc_ptrs, sizeof(int) * ((size_t)n_nodes + 1)));
+    CK(ensure(ctx->b_nc_data, sizeof(int) * n_nc));
+    CK(ensure(ctx->b_nbr, sizeof(int) * 3 * (size_t)n_cells));
+    CK(ensure(ctx->b_cells, sizeof(CellRec) * (size_t)n_cells));
+    CK(ensure(ctx->b_edges, sizeof(EdgeRec) * 3 * (size_t)n_cells));
+    CK(ensure(ctx->b_qual, sizeof(float) * (size_t)n_cells));
+    CK(ensure(ctx->b_bdist, sizeof(float) * (size_t)n_cells));
+    CK(ensure(ctx->b_sc, sizeof(MeshScalars)));
+    // stage the 1-based tables through a scratch buffer and convert on the device
+    DevBuf scratch;
+    size_t max_tab = std::max(std::max((size_t)3 * n_cells, (size_t)n_nodes + 1), n_nc);
+    CK(ensure(scratch, sizeof(int32_t) * max_tab));
+    CK(cudaMemcpyAsync(ctx->b_xy.p, xy, sizeof(double) * 2 * (size_t)n_nodes, cudaMemcpyHostToDevice, st));
+    struct {
+        const int32_t *src;
+        void *dst;
+        size_t n;
+    } tabs[3] = {{cell_data, ctx->b_cell_nodes.p, (size_t)3 * n_cells},
+                 {node_cell_ptrs, ctx->b_nc_ptrs.p, (size_t)n_nodes + 1},
+                 {node_cell_data, ctx->b_nc_data.p, n_nc}};
+    for (auto &tb : tabs) {
+        CK(cudaMemcpyAsync(scratch.p, tb.src, sizeof(int32_t) * tb.n, cudaMemcpyHostToDevice, st));
+        k_to_zero_based<<<blocks_for((long long)tb.n, 256), 256, 0, st>>>((const int32_t *)scratch.p, (int *)tb.dst, (long long)tb.n);
+        CK(cudaStreamSynchronize(st));  // host source may be pageable; scratch is reused
+    }
+    release(scratch);
+
+    DevMesh &m = ctx->m;
+    m.n_nodes = n_nodes;
+    m.n_cells = n_cells;
+    m.xy = (const double2 *)ctx->b_xy.p;
+    m.cell_nodes = (const int *)ctx->b_cell_nodes.p;
+    m.nc_ptrs = (const int *)ctx->b_nc_ptrs.p;
+    m.nc_data = (const int *)ctx->b_nc_data.p;
+    m.cells = (const CellRec *)ctx->b_cells.p;
+    m.edges = (const EdgeRec *)ctx->b_edges.p;
+    m.bbmin[0] = bb_min[0];
+    m.bbmin[1] = bb_min[1];
+    m.bbmax[0] = bb_max[0];
+    m.bbmax[1] = bb_max[1];
+    // node grid: ~2 nodes per bin
+    double w = bb_max[0] - bb_min[0], h = bb_max[1] - bb_min[1];
+    if (!(w > 0 && h > 0)) return fail(ctx, RT_ERR_ARG, "rt_mesh_upload: empty bounding box");
+    double gh = sqrt(w * h / ((double)n_nodes / 2.0));
+    m.gx = std::max(1, (int)ceil(w / gh));
+    m.gy = std::max(1, (int)ceil(h / gh));
+    m.g0x = bb_min[0];
+    m.g0y = bb_min[1];
+    m.gh = gh;
+    m.ginv = 1.0 / gh;
+    size_t n_bins = (size_t)m.gx * m.gy;
+    CK(ensure(ctx->b_grid_ptrs, sizeof(int) * (n_bins + 1)));
+    CK(ensure(ctx->b_grid_nodes, sizeof(int) * (size_t)n_nodes));
+    m.grid_ptrs = (const int *)ctx->b_grid_ptrs.p;
+    m.grid_nodes = (const int *)ctx->b_grid_nodes.p;
+
+    k_neighbours<<<blocks_for(3LL * n_cells, 256), 256, 0, st>>>(n_cells, m.cell_nodes, m.nc_ptrs, m.nc_data, (int *)ctx->b_nbr.p);
+    CK(cudaMemsetAsync(ctx->b_sc.p, 0, sizeof(MeshScalars), st));
+    k_cell_records<<<blocks_for(n_cells, 128), 128, 0, st>>>(m, (const int *)ctx->b_nbr.p, (CellRec *)ctx->b_cells.p,
+                                                             (EdgeRec *)ctx->b_edges.p, (float *)ctx->b_qual.p,
+                                                             (float *)ctx->b_bdist.p, (MeshScalars *)ctx->b_sc.p);
+    // grid: count -> scan -> fill
+    DevBuf counts, cursor;
+    CK(ensure(counts, sizeof(int) * n_bins));
+    CK(ensure(cursor, sizeof(int) * n_bins));
+    CK(cudaMemsetAsync(counts.p, 0, sizeof(int) * n_bins, st));
+    CK(cudaMemsetAsync(cursor.p, 0, sizeof(int) * n_bins, st));
+    k_grid_count<<<blocks_for(n_nodes, 256), 256, 0, st>>>(m, (int *)counts.p);
+    CK((exclusive_scan<int, int>(ctx, (const int *)counts.p, (int *)ctx->b_grid_ptrs.p, (long long)n_bins)));
+    k_grid_fill<<<blocks_for(n_nodes, 256), 256, 0, st>>>(m, m.grid_ptrs, (int *)cursor.p, (int *)ctx->b_grid_nodes.p);
+    CK(cudaGetLastError());
+    MeshScalars sc;
+    CK(cudaMemcpyAsync(&sc, ctx->b_sc.p, sizeof(sc), cudaMemcpyDeviceToHost, st));
+    ctx->phase_ms[0] = toc(ctx);
+    CK(cudaStreamSynchronize(st));
+    release(counts);
+    release(cursor);
+    ctx->smax = sc.smax;
+    ctx->lmax = sc.lmax;
+    ctx->clear_tiny = -1.0;
+    ctx->has_mesh = true;
+    ctx->traced = false;
+    ctx->segmented = false;
+    return RT_OK;
+}
+
+extern "C" int rt_mesh_neighbours(rt_ctx *ctx, int32_t *cell_nbr) {
+    if (!ctx || !ctx->has_mesh || !cell_nbr) return fail(ctx, RT_ERR_ARG, "rt_mesh_neighbours: no mesh");
+    CK(cudaSetDevice(ctx->device));
+    size_t n = 3 * (size_t)ctx->m.n_cells;
+    CK(cudaMemcpy(cell_nbr, ctx->b_nbr.p, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) cell_nbr[i] += 1;  // 1-based, 0 = boundary
+    return RT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// trace!
+// ------------------------------------------------------------------------------------------------------
+static int upload_angle_tables(rt_ctx *ctx, int32_t n2, const int64_t *nx, const int64_t *ny, const double *phi,
+                               const double *sin_phi, const double *cos_phi, const double *tan_phi, const double *dxe,
+                               const double *dye) {
+    if (n2 < 2 || (n2 % 2) != 0) return fail(ctx, RT_ERR_ARG, "n_azim_2 must be a positive even number");
+    std::vector<double> hd(7 * (size_t)n2, 0.0);
+    const double *cols[6] = {phi, sin_phi, cos_phi, tan_phi, dxe, dye};
+    for (int q = 0; q < 6; ++q)
+        if (cols[q]) memcpy(&hd[(size_t)q * n2], cols[q], sizeof(double) * n2);
+    std::vector<long long> hi(3 * (size_t)n2 + 1, 0);
+    ctx->h_base.assign((size_t)n2 + 1, 0);
+    for (int i = 0; i < n2; ++i) {
+        if (nx[i] < 1 || ny[i] < 1) return fail(ctx, RT_ERR_ARG, "n_tracks_x/y must be >= 1");
+        hi[i] = nx[i];
+        hi[n2 + i] = ny[i];
+        ctx->h_base[i + 1] = ctx->h_base[i] + nx[i] + ny[i];
+    }
+    for (int i = 0; i <= n2; ++i) hi[2 * (size_t)n2 + i] = ctx->h_base[i];
+    CK(ensure(ctx->b_ang_d, sizeof(double) * hd.size()));
+    CK(ensure(ctx->b_ang_i, sizeof(long long) * hi.size()));
+    CK(cudaMemcpyAsync(ctx->b_ang_d.p, hd.data(), sizeof(double) * hd.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->b_ang_i.p, hi.data(), sizeof(long long) * hi.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n2 = n2;
+    ctx->h_phi.assign(phi, phi + n2);
+    ctx->has_delta = false;
+    return RT_OK;
+}
+
+static void fill_trace_params(rt_ctx *ctx, TraceParams &P, const int32_t bcs[4]) {
+    int n2 = ctx->n2;
+    const double *d = (const double *)ctx->b_ang_d.p;
+    const long long *li = (const long long *)ctx->b_ang_i.p;
+    P.n2 = n2;
+    P.n4 = n2 / 2;
+    P.nx = li;
+    P.ny = li + n2;
+    P.base = li + 2 * n2;
+    P.phi = d;
+    P.tanp = d + 3 * n2;
+    P.dxe = d + 4 * n2;
+    P.dye = d + 5 * n2;
+    for (int q = 0; q < 4; ++q) P.bcs[q] = bcs ? bcs[q] : 0;
+    for (int q = 0; q < 2; ++q) {
+        P.bbmin[q] = ctx->m.bbmin[q];
+        P.bbmax[q] = ctx->m.bbmax[q];
+    }
+    P.len_only = nullptr;
+    P.err = (unsigned long long *)ctx->b_err.p;
+}
+
+extern "C" int rt_trace(rt_ctx *ctx, int32_t n_azim_2, const int64_t *n_tracks_x, const int64_t *n_tracks_y, const double *phi,
+                        const double *sin_phi, const double *cos_phi, const double *tan_phi, const double *dx_eff,
+                        const double *dy_eff, const int32_t bcs[4], int64_t uid_begin, int64_t uid_end) {
+    if (!ctx || !ctx->has_mesh) return fail(ctx, RT_ERR_ARG, "rt_trace: upload a mesh first");
+    if (!n_tracks_x || !n_tracks_y || !phi || !sin_phi || !cos_phi || !tan_phi || !dx_eff || !dy_eff || !bcs)
+        return fail(ctx, RT_ERR_ARG, "rt_trace: null table");
+    for (int q = 0; q < 4; ++q)
+        if (bcs[q] < 0 || bcs[q] > 2) return fail(ctx, RT_ERR_ARG, "rt_trace: bad boundary condition code");
+    CK(cudaSetDevice(ctx->device));
+    int rc = upload_angle_tables(ctx, n_azim_2, n_tracks_x, n_tracks_y, phi, sin_phi, cos_phi, tan_phi, dx_eff, dy_eff);
+    if (rc) return rc;
+    long long n_total = ctx->h_base[n_azim_2];
+    if (uid_begin < 1 || uid_end > n_total + 1 || uid_end < uid_begin)
+        return fail(ctx, RT_ERR_ARG, "rt_trace: uid range [%lld,%lld) outside [1,%lld]", (long long)uid_begin, (long long)uid_end,
+                    n_total + 1);
+    long long n = uid_end - uid_begin;
+    ctx->uid_begin = uid_begin;
+    ctx->n_shard = n;
+    ctx->traced = false;
+    ctx->segmented = false;
+    size_t nn = (size_t)std::max<long long>(n, 1);
+    CK(ensure(ctx->b_trk_d, sizeof(double) * 8 * nn));
+    CK(ensure(ctx->b_trk_i, sizeof(int) * nn));
+    CK(ensure(ctx->b_trk_l, sizeof(long long) * 3 * nn));
+    CK(ensure(ctx->b_trk_c, 4 * nn));
+    CK(ensure(ctx->b_err, sizeof(unsigned long long)));
+    double *d = (double *)ctx->b_trk_d.p;
+    TrackSoA &t = ctx->t;
+    t.px = d;
+    t.py = d + nn;
+    t.qx = d + 2 * nn;
+    t.qy = d + 3 * nn;
+    t.len = d + 4 * nn;
+    t.a = d + 5 * nn;
+    t.b = d + 6 * nn;
+    t.c = d + 7 * nn;
+    t.azim = (int *)ctx->b_trk_i.p;
+    long long *l = (long long *)ctx->b_trk_l.p;
+    t.track_idx = l;
+    t.next_fwd = l + nn;
+    t.next_bwd = l + 2 * nn;
+    signed char *c = (signed char *)ctx->b_trk_c.p;
+    t.bc_fwd = c;
+    t.bc_bwd = c + nn;
+    t.dir_fwd = c + 2 * nn;
+    t.dir_bwd = c + 3 * nn;
+    CK(cudaMemsetAsync(ctx->b_err.p, 0xff, sizeof(unsigned long long), ctx->stream));
+    TraceParams P;
+    fill_trace_params(ctx, P, bcs);
+    P.uid_begin = uid_begin;
+    P.n = n;
+    P.t = t;
+    tic(ctx);
+    if (n > 0) k_trace<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(P);
+    CK(cudaGetLastError());
+    unsigned long long err = 0;
+    CK(cudaMemcpyAsync(&err, ctx->b_err.p, sizeof(err), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->phase_ms[1] = toc(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (err != ~0ULL) {
+        long long uid = (long long)(err >> 4);
+        int code = (int)(err & 15);
+        if (code == TRACE_E_NO_EXIT) return fail(ctx, RT_ERR_NO_EXIT, "DomainError: could not found track exit point. (uid %lld)", uid);
+        if (code == TRACE_E_NOT_ON_BOUNDARY) return fail(ctx, RT_ERR_NOT_ON_BOUNDARY, "Point do not lie in the boundary. (uid %lld)", uid);
+        return fail(ctx, RT_ERR_BC_MISMATCH, "Boundaries do not match! (uid %lld)", uid);
+    }
+    ctx->traced = true;
+    return RT_OK;
+}
+
+template <typename T>
+static int fetch_col(rt_ctx *ctx, const T *dev, std::vector<T> &host, size_t n) {
+    host.resize(n);
+    CK(cudaMemcpy(host.data(), dev, sizeof(T) * n, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+extern "C" int rt_tracks_download(rt_ctx *ctx, int64_t *azim_idx, int64_t *track_idx, double *p, double *q, double *phi,
+                                  double *len, double *abc, int8_t *bc_fwd, int8_t *bc_bwd, int8_t *dir_fwd, int8_t *dir_bwd,
+                                  int64_t *next_fwd_uid, int64_t *next_bwd_uid) {
+    if (!ctx || !ctx->traced) return fail(ctx, RT_ERR_NOT_TRACED, "rt_tracks_download: call rt_trace first");
+    CK(cudaSetDevice(ctx->device));
+    size_t n = (size_t)ctx->n_shard;
+    if (n == 0) return RT_OK;
+    const TrackSoA &t = ctx->t;
+    std::vector<double> c0, c1, c2;
+    int rc;
+    if (p) {
+        if ((rc = fetch_col(ctx, t.px, c0, n)) || (rc = fetch_col(ctx, t.py, c1, n))) return rc;
+        for (size_t i = 0; i < n; ++i) {
+            p[2 * i] = c0[i];
+            p[2 * i + 1] = c1[i];
+        }
+    }
+    if (q) {
+        if ((rc = fetch_col(ctx, t.qx, c0, n)) || (rc = fetch_col(ctx, t.qy, c1, n))) return rc;
+        for (size_t i = 0; i < n; ++i) {
+            q[2 * i] = c0[i];
+            q[2 * i + 1] = c1[i];
+        }
+    }
+    if (abc) {
+        if ((rc = fetch_col(ctx, t.a, c0, n)) || (rc = fetch_col(ctx, t.b, c1, n)) || (rc = fetch_col(ctx, t.c, c2, n))) return rc;
+        for (size_t i = 0; i < n; ++i) {
+            abc[3 * i] = c0[i];
+            abc[3 * i + 1] = c1[i];
+            abc[3 * i + 2] = c2[i];
+        }
+    }
+    if (len) CK(cudaMemcpy(len, t.len, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (azim_idx || phi) {
+        std::vector<int> az;
+        if ((rc = fetch_col(ctx, t.azim, az, n))) return rc;
+        for (size_t i = 0; i < n; ++i) {
+            if (azim_idx) azim_idx[i] = az[i] + 1;
+            if (phi) phi[i] = ctx->h_phi[az[i]];
+        }
+    }
+    if (track_idx) CK(cudaMemcpy(track_idx, t.track_idx, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+    if (next_fwd_uid) CK(cudaMemcpy(next_fwd_uid, t.next_fwd, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+    if (next_bwd_uid) CK(cudaMemcpy(next_bwd_uid, t.next_bwd, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+    if (bc_fwd) CK(cudaMemcpy(bc_fwd, t.bc_fwd, n, cudaMemcpyDeviceToHost));
+    if (bc_bwd) CK(cudaMemcpy(bc_bwd, t.bc_bwd, n, cudaMemcpyDeviceToHost));
+    if (dir_fwd) CK(cudaMemcpy(dir_fwd, t.dir_fwd, n, cudaMemcpyDeviceToHost));
+    if (dir_bwd) CK(cudaMemcpy(dir_bwd, t.dir_bwd, n, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+__global__ void k_split_points(const double *cum /* n+1 */, long long n, int n_parts, long long *bounds) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_parts) return;
+    if (r == 0) {
+        bounds[0] = 1;
+        return;
+    }
+    if (r == n_parts) {
+        bounds[r] = n + 1;
+        return;
+    }
+    double target = cum[n] * ((double)r / (double)n_parts);
+    long long lo = 0, hi = n;  // first index with cum[idx] >= target
+    while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        if (cum[mid] < target)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    bounds[r] = lo + 1;
+}
+
+extern "C" int rt_plan_shards(rt_ctx *ctx, int32_t n_azim_2, const int64_t *n_tracks_x, const int64_t *n_tracks_y,
+                              const double *phi, const double *tan_phi, const double *dx_eff, const double *dy_eff,
+                              int32_t n_parts, int64_t *bounds) {
+    if (!ctx || !ctx->has_mesh) return fail(ctx, RT_ERR_ARG, "rt_plan_shards: upload a mesh first");
+    if (n_parts < 1 || !bounds || !phi || !tan_phi || !dx_eff || !dy_eff) return fail(ctx, RT_ERR_ARG, "rt_plan_shards: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    int rc = upload_angle_tables(ctx, n_azim_2, n_tracks_x, n_tracks_y, phi, nullptr, nullptr, tan_phi, dx_eff, dy_eff);
+    if (rc) return rc;
+    ctx->traced = false;
+    ctx->segmented = false;
+    long long n = ctx->h_base[n_azim_2];
+    DevBuf lens, cum, db;
+    CK(ensure(lens, sizeof(double) * (size_t)n));
+    CK(ensure(cum, sizeof(double) * ((size_t)n + 1)));
+    CK(ensure(db, sizeof(long long) * ((size_t)n_parts + 1)));
+    CK(ensure(ctx->b_err, sizeof(unsigned long long)));
+    TraceParams P;
+    fill_trace_params(ctx, P, nullptr);
+    P.uid_begin = 1;
+    P.n = n;
+    P.t = TrackSoA{};
+    P.len_only = (double *)lens.p;
+    k_trace<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(P);
+    CK((exclusive_scan<double, double>(ctx, (const double *)lens.p, (double *)cum.p, n)));
+    k_split_points<<<blocks_for(n_parts + 1, 64), 64, 0, ctx->stream>>>((const double *)cum.p, n, n_parts, (long long *)db.p);
+    CK(cudaGetLastError());
+    std::vector<long long> hb((size_t)n_parts + 1);
+    CK(cudaMemcpyAsync(hb.data(), db.p, sizeof(long long) * hb.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int r = 0; r <= n_parts; ++r) bounds[r] = hb[r];
+    for (int r = 1; r <= n_parts; ++r) bounds[r] = std::max(bounds[r], bounds[r - 1]);
+    release(lens);
+    release(cum);
+    release(db);
+    return RT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// segmentize!
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_first_bad(const int *status, long long n, unsigned long long *out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n && status[i] != 0) atomicMin(out, ((unsigned long long)i << 4) | (unsigned long long)(status[i] & 15));
+}
+
+__global__ void k_normalise(const double *in, double *out, int n, double denom) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] / denom;  // volumes ./= n_azim_2, src/trackgenerator.jl:386
+}
+
+extern "C" int rt_set_segment_capacity(rt_ctx *ctx, int64_t max_segments_resident) {
+    if (!ctx || max_segments_resident < 0) return RT_ERR_ARG;
+    ctx->cap_cfg = max_segments_resident;
+    return RT_OK;
+}
+
+static int ensure_segment_buffers(rt_ctx *ctx, long long want) {
+    if (want <= ctx->cap && ctx->b_seg_d.p) return RT_OK;
+    release(ctx->b_seg_d);
+    release(ctx->b_seg_e);
+    ctx->cap = 0;
+    size_t n = (size_t)std::max<long long>(want, 1);
+    CK(ensure(ctx->b_seg_d, sizeof(double) * 5 * n));
+    CK(ensure(ctx->b_seg_e, sizeof(int) * n));
+    double *d = (double *)ctx->b_seg_d.p;
+    ctx->s_px = d;
+    ctx->s_py = d + n;
+    ctx->s_qx = d + 2 * n;
+    ctx->s_qy = d + 3 * n;
+    ctx->s_len = d + 4 * n;
+    ctx->s_elem = (int *)ctx->b_seg_e.p;
+    ctx->cap = (long long)n;
+    return RT_OK;
+}
+
+extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rtol, int32_t max_iter, const double *delta_eff,
+                             uint32_t flags, rt_batch_cb cb, void *cb_user, int64_t *n_segments_total, int64_t *first_bad_uid,
+                             int32_t *bad_status) {
+    if (!ctx) return RT_ERR_ARG;
+    if (!ctx->traced)
+        return fail(ctx, RT_ERR_NOT_TRACED, "Segmentation is intended after tracing. Please, call `trace!` first!");
+    if (k < 1 || max_iter < 0) return fail(ctx, RT_ERR_ARG, "rt_segmentize: bad k / max_iter");
+    const bool want_vol = !(flags & RT_SEG_NO_VOLUMES);
+    if (want_vol && !delta_eff) return fail(ctx, RT_ERR_ARG, "rt_segmentize: delta_eff is required unless RT_SEG_NO_VOLUMES");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const long long n = ctx->n_shard;
+    const int n2 = ctx->n2;
+    DevMesh &m = ctx->m;
+    ctx->segmented = false;
+    ctx->vol_valid = false;
+
+    if (ctx->clear_tiny != tiny_step) {
+        k_finalize_clear<<<blocks_for(m.n_cells, 128), 128, 0, st>>>(m, (CellRec *)ctx->b_cells.p, (const float *)ctx->b_qual.p,
+                                                                     (const float *)ctx->b_bdist.p, (const MeshScalars *)ctx->b_sc.p,
+                                                                     tiny_step);
+        CK(cudaGetLastError());
+        ctx->clear_tiny = tiny_step;
+    }
+    if (want_vol) {
+        CK(cudaMemcpyAsync((double *)ctx->b_ang_d.p + 6 * (size_t)n2, delta_eff, sizeof(double) * n2, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->has_delta = true;
+        CK(ensure(ctx->b_vol, sizeof(double) * (size_t)m.n_cells));
+        CK(cudaMemsetAsync(ctx->b_vol.p, 0, sizeof(double) * (size_t)m.n_cells, st));
+    }
+    size_t nn = (size_t)std::max<long long>(n, 1);
+    CK(ensure(ctx->b_count, sizeof(int) * nn));
+    CK(ensure(ctx->b_status, sizeof(int) * nn));
+    CK(ensure(ctx->b_offsets, sizeof(long long) * (nn + 1)));
+    CK(ensure(ctx->b_counters, sizeof(unsigned long long) * 4));
+    CK(ensure(ctx->b_bad, sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(ctx->b_counters.p, 0, sizeof(unsigned long long) * 4, st));
+    CK(cudaMemsetAsync(ctx->b_bad.p, 0xff, sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(ctx->b_offsets.p, 0, sizeof(long long) * (nn + 1), st));
+
+    WalkParams P{};
+    P.m = m;
+    P.t = ctx->t;
+    const double *ad = (const double *)ctx->b_ang_d.p;
+    P.ang.phi = ad;
+    P.ang.sinp = ad + n2;
+    P.ang.cosp = ad + 2 * n2;
+    P.ang.delta_eff = ad + 6 * n2;
+    P.tiny = tiny_step;
+    P.rtol = rtol;
+    P.k = k;
+    P.max_iter = max_iter;
+    P.flags = flags;
+    // fast path only accepts chords that are certainly not dropped by isapprox(p, q) (src/track.jl:156) and long
+    // enough for the re-location argument: l > max(8*tiny, rtol * largest possible |point|)
+    double nb = hypot(fmax(fabs(m.bbmin[0]), fabs(m.bbmax[0])), fmax(fabs(m.bbmin[1]), fabs(m.bbmax[1])));
+    P.lmin = fmax(8.0 * tiny_step, kRtol * nb * (1.0 + 1e-6) + 1e-300);
+    P.count = (int *)ctx->b_count.p;
+    P.status = (int *)ctx->b_status.p;
+    P.offsets = (const long long *)ctx->b_offsets.p;
+    P.counters = (unsigned long long *)ctx->b_counters.p;
+    const bool count_only = (flags & RT_SEG_COUNT_ONLY) != 0;
+    double launches = 0;
+
+    // ---- count pass
+    tic(ctx);
+    P.trk_begin = 0;
+    P.n_tracks = n;
+    P.vol = (want_vol && count_only) ? (double *)ctx->b_vol.p : nullptr;
+    if (n > 0) {
+        k_walk<false><<<blocks_for(n, 128), 128, 0, st>>>(P);
+        launches += 1;
+    }
+    CK(cudaGetLastError());
+    ctx->phase_ms[2] = toc(ctx);
+    // ---- scan
+    tic(ctx);
+    long long total = 0;
+    unsigned long long bad = ~0ULL;
+    if (n > 0) {
+        CK((exclusive_scan<int, long long>(ctx, (const int *)ctx->b_count.p, (long long *)ctx->b_offsets.p, n)));
+        k_first_bad<<<blocks_for(n, 256), 256, 0, st>>>((const int *)ctx->b_status.p, n, (unsigned long long *)ctx->b_bad.p);
+        launches += 4;
+        CK(cudaMemcpyAsync(&total, (long long *)ctx->b_offsets.p + n, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&bad, ctx->b_bad.p, sizeof(bad), cudaMemcpyDeviceToHost, st));
+    }
+    ctx->phase_ms[3] = toc(ctx);
+    CK(cudaStreamSynchronize(st));
+    ctx->total_segments = total;
+    if (n_segments_total) *n_segments_total = total;
+    if (first_bad_uid) *first_bad_uid = 0;
+    if (bad_status) *bad_status = 0;
+
+    // ---- fill pass (possibly in uid batches over a recycled buffer)
+    ctx->phase_ms[4] = 0.0;
+    ctx->res_trk_begin = ctx->res_trk_end = 0;
+    ctx->res_off_base = 0;
+    ctx->res_nseg = 0;
+    if (!count_only && n > 0) {
+        long long cap = total;
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        long long fit = (long long)((double)(free_b + ctx->b_seg_d.bytes + ctx->b_seg_e.bytes) * 0.92 / 44.0);
+        if (ctx->cap_cfg > 0) cap = std::min(cap, (long long)ctx->cap_cfg);
+        cap = std::min(cap, fit);
+        int rc = ensure_segment_buffers(ctx, cap);
+        if (rc) return rc;
+        P.opx = ctx->s_px;
+        P.opy = ctx->s_py;
+        P.oqx = ctx->s_qx;
+        P.oqy = ctx->s_qy;
+        P.olen = ctx->s_len;
+        P.oelem = ctx->s_elem;
+        P.vol = want_vol ? (double *)ctx->b_vol.p : nullptr;
+        P.counters = nullptr;
+        std::vector<long long> h_off;
+        if (total > cap) {
+            h_off.resize((size_t)n + 1);
+            CK(cudaMemcpy(h_off.data(), ctx->b_offsets.p, sizeof(long long) * ((size_t)n + 1), cudaMemcpyDeviceToHost));
+        }
+        tic(ctx);
+        long long b = 0;
+        while (b < n) {
+            long long e = n;
+            if (total > cap) {
+                // largest e with off[e] - off[b] <= cap
+                long long lim = h_off[b] + cap;
+                e = (long long)(std::upper_bound(h_off.begin() + b, h_off.end(), lim) - h_off.begin()) - 1;
+                if (e <= b) return fail(ctx, RT_ERR_NOMEM, "rt_segmentize: one track needs more than the segment capacity");
+            }
+            P.trk_begin = b;
+            P.n_tracks = e - b;
+            P.offset_base = total > cap ? h_off[b] : 0;
+            k_walk<true><<<blocks_for(e - b, 128), 128, 0, st>>>(P);
+            launches += 1;
+            CK(cudaGetLastError());
+            ctx->res_trk_begin = b;
+            ctx->res_trk_end = e;
+            ctx->res_off_base = P.offset_base;
+            ctx->res_nseg = (total > cap ? h_off[e] : total) - P.offset_base;
+            if (cb) {
+                rt_batch bt;
+                int rcb = rt_segments_device(ctx, &bt);
+                if (rcb) return rcb;
+                if (cb(&bt, cb_user)) return fail(ctx, RT_ERR_ARG, "rt_segmentize: batch callback asked to stop");
+            }
+            b = e;
+        }
+        ctx->phase_ms[4] = toc(ctx);
+    }
+    unsigned long long hc[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(hc, ctx->b_counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->stats[0] = launches;
+    for (int q = 0; q < 4; ++q) ctx->stats[1 + q] = (double)hc[q];
+    ctx->stats[5] = ctx->phase_ms[2];
+    ctx->stats[6] = ctx->phase_ms[4];
+    ctx->stats[7] = ctx->phase_ms[3];
+    ctx->segmented = true;
+    ctx->vol_valid = want_vol;
+    if (bad != ~0ULL) {
+        long long idx = (long long)(bad >> 4);
+        int stt = (int)(bad & 15);
+        if (first_bad_uid) *first_bad_uid = ctx->uid_begin + idx;
+        if (bad_status) *bad_status = stt;
+        const char *msg = stt == RT_TRACK_TRY_K
+                              ? "Try increasing `k`. If the problem persists, raise an issue, this might be a case that hasn't been presented before."
+                              : (stt == RT_TRACK_LENGTH ? "has a length that do not match the sum of its segments lengths with the provided tolerance `rtol`."
+                                                        : "walk failed");
+        return fail(ctx, RT_ERR_TRACK, "Track with `uid` %lld: %s (status %d)", ctx->uid_begin + idx, msg, stt);
+    }
+    return RT_OK;
+}
+
+extern "C" int rt_segment_offsets(rt_ctx *ctx, int64_t *offsets, int32_t *status) {
+    if (!ctx || !ctx->segmented) return fail(ctx, RT_ERR_ARG, "rt_segment_offsets: call rt_segmentize first");
+    CK(cudaSetDevice(ctx->device));
+    size_t n = (size_t)ctx->n_shard;
+    if (offsets) CK(cudaMemcpy(offsets, ctx->b_offsets.p, sizeof(long long) * (n + 1), cudaMemcpyDeviceToHost));
+    if (status && n) CK(cudaMemcpy(status, ctx->b_status.p, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+extern "C" int rt_segments_download(rt_ctx *ctx, double *px, double *py, double *qx, double *qy, double *len, int32_t *element) {
+    if (!ctx || !ctx->segmented) return fail(ctx, RT_ERR_ARG, "rt_segments_download: call rt_segmentize first");
+    CK(cudaSetDevice(ctx->device));
+    size_t n = (size_t)ctx->res_nseg;
+    if (n == 0) return RT_OK;
+    cudaStream_t st = ctx->stream;
+    if (px) CK(cudaMemcpyAsync(px, ctx->s_px, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    if (py) CK(cudaMemcpyAsync(py, ctx->s_py, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    if (qx) CK(cudaMemcpyAsync(qx, ctx->s_qx, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    if (qy) CK(cudaMemcpyAsync(qy, ctx->s_qy, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    if (len) CK(cudaMemcpyAsync(len, ctx->s_len, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    if (element) CK(cudaMemcpyAsync(element, ctx->s_elem, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return RT_OK;
+}
+
+extern "C" int rt_segments_device(rt_ctx *ctx, rt_batch *view) {
+    if (!ctx || !view) return RT_ERR_ARG;
+    view->uid_begin = ctx->uid_begin + ctx->res_trk_begin;
+    view->uid_end = ctx->uid_begin + ctx->res_trk_end;
+    view->n_segments = ctx->res_nseg;
+    view->d_offsets = (const int64_t *)ctx->b_offsets.p;
+    view->offset_base = ctx->res_off_base;
+    view->d_px = ctx->s_px;
+    view->d_py = ctx->s_py;
+    view->d_qx = ctx->s_qx;
+    view->d_qy = ctx->s_qy;
+    view->d_len = ctx->s_len;
+    view->d_element = ctx->s_elem;
+    view->stream = (void *)ctx->stream;
+    return RT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// volumes + NCCL
+// ------------------------------------------------------------------------------------------------------
+static int load_nccl(rt_ctx *ctx) {
+    NcclApi &a = ctx->nccl;
+    if (a.lib) return RT_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        a.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (a.lib) break;
+    }
+    if (!a.lib) return fail(ctx, RT_ERR_NCCL, "dlopen(libnccl.so.2) failed: %s", dlerror());
+    a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.lib, "ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.lib, "ncclCommInitRank");
+    a.AllReduce = (decltype(a.AllReduce))dlsym(a.lib, "ncclAllReduce");
+    a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.lib, "ncclCommDestroy");
+    a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.lib, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.CommDestroy) return fail(ctx, RT_ERR_NCCL, "NCCL symbols missing");
+    return RT_OK;
+}
+
+extern "C" int rt_comm_unique_id(rt_ctx *ctx, char id[128]) {
+    if (!ctx || !id) return RT_ERR_ARG;
+    int rc = load_nccl(ctx);
+    if (rc) return rc;
+    ncclUniqueId u;
+    ncclResult_t r = ctx->nccl.GetUniqueId(&u);
+    if (r != 0) return fail(ctx, RT_ERR_NCCL, "ncclGetUniqueId: %s", ctx->nccl.GetErrorString ? ctx->nccl.GetErrorString(r) : "?");
+    memcpy(id, u.internal, 128);
+    return RT_OK;
+}
+
+extern "C" int rt_comm_init(rt_ctx *ctx, int32_t n_ranks, int32_t rank, const char id[128]) {
+    if (!ctx || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return RT_ERR_ARG;
+    int rc = load_nccl(ctx);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    ncclUniqueId u;
+    memcpy(u.internal, id, 128);
+    ncclResult_t r = ctx->nccl.CommInitRank(&ctx->comm, n_ranks, u, rank);
+    if (r != 0) return fail(ctx, RT_ERR_NCCL, "ncclCommInitRank: %s", ctx->nccl.GetErrorString ? ctx->nccl.GetErrorString(r) : "?");
+    ctx->n_ranks = n_ranks;
+    ctx->rank = rank;
+    return RT_OK;
+}
+
+extern "C" int rt_volumes(rt_ctx *ctx, double *volumes) {
+    if (!ctx || !ctx->segmented || !ctx->vol_valid) return fail(ctx, RT_ERR_ARG, "rt_volumes: run rt_segmentize with volumes enabled first");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int nc = ctx->m.n_cells;
+    CK(ensure(ctx->b_voln, sizeof(double) * (size_t)nc));
+    tic(ctx);
+    const double *src = (const double *)ctx->b_vol.p;
+    if (ctx->comm) {
+        // the ONLY collective of the path: sum of per-element delta*len over the uid shards
+        ncclResult_t r = ctx->nccl.AllReduce(ctx->b_vol.p, ctx->b_voln.p, (size_t)nc, ncclFloat64, ncclSum, ctx->comm, st);
+        if (r != 0) return fail(ctx, RT_ERR_NCCL, "ncclAllReduce: %s", ctx->nccl.GetErrorString ? ctx->nccl.GetErrorString(r) : "?");
+        src = (const double *)ctx->b_voln.p;
+    }
+    k_normalise<<<blocks_for(nc, 256), 256, 0, st>>>(src, (double *)ctx->b_voln.p, nc, (double)ctx->n2);
+    CK(cudaGetLastError());
+    ctx->phase_ms[5] = toc(ctx);
+    if (volumes) CK(cudaMemcpy(volumes, ctx->b_voln.p, sizeof(double) * (size_t)nc, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+extern "C" int rt_stats(rt_ctx *ctx, double stats[8]) {
+    if (!ctx || !stats) return RT_ERR_ARG;
+    memcpy(stats, ctx->stats, sizeof(ctx->stats));
+    return RT_OK;
+}
+
+extern "C" int rt_phase_ms(rt_ctx *ctx, double ms[6]) {
+    if (!ctx || !ms) return RT_ERR_ARG;
+    memcpy(ms, ctx->phase_ms, sizeof(ctx->phase_ms));
+    return RT_OK;
+}

@@ -1,0 +1,75 @@
+"""Multi-GPU plumbing: one process per GPU, tracks sharded by contiguous uid range (equal total track length
+per rank), mesh replicated, ONE collective -- the NCCL all-reduce of per-element sum(delta*len) inside
+rt_volumes (reference src/trackgenerator.jl:378-386 is the serial loop it replaces).  torch.distributed is only
+used to ship the 128-byte NCCL unique id; the communicator lives inside librt_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+
+
+def track_lengths(tg) -> np.ndarray:
+    """Lengths of all tracks in uid order (vectorised restatement of src/trackgenerator.jl:188-226; only used to
+    balance shards, not for results). Needs tg.azimuthal_quadrature.phis, i.e. the tables of trace_."""
+    from .api import nazim2, nazim4
+
+    aq = tg.azimuthal_quadrature
+    n2, n4 = nazim2(aq), nazim4(aq)
+    dx, dy = tg.mesh.width, tg.mesh.height
+    out = []
+    for i in range(1, n2 + 1):
+        nx, ny = int(tg.n_tracks_x[i - 1]), int(tg.n_tracks_y[i - 1])
+        right = i <= n4
+        dxe, dye = dx / nx, dy / ny
+        j = np.arange(1, nx + ny + 1, dtype=np.float64)
+        onx = j <= nx
+        px = np.where(onx, np.where(right, dxe * (nx - j + 0.5), dxe * (j - 0.5)), 0.0 if right else dx)
+        py = np.where(onx, 0.0, dye * (j - nx - 0.5))
+        m = np.tan(aq.phis[i - 1])
+        qx = px - (py - dy) / m
+        qy = np.full_like(qx, dy)
+        bad = ~((0 <= qx) & (qx <= dx))
+        if right:
+            qy = np.where(bad, py + m * (dx - px), qy)
+            qx = np.where(bad, dx, qx)
+        else:
+            qy = np.where(bad, py - m * px, qy)
+            qx = np.where(bad, 0.0, qx)
+        out.append(np.hypot(px - qx, py - qy))
+    return np.concatenate(out)
+
+
+def plan_shards(tg, n_parts: int) -> np.ndarray:
+    """bounds[r] .. bounds[r+1] (1-based uids, end exclusive) with equal total track length per part."""
+    lens = track_lengths(tg)
+    cum = np.concatenate([[0.0], np.cumsum(lens)])
+    targets = cum[-1] * (np.arange(1, n_parts) / n_parts)
+    inner = np.searchsorted(cum, targets, side="left") + 1
+    bounds = np.concatenate([[1], inner, [lens.size + 1]]).astype(np.int64)
+    return np.maximum.accumulate(bounds)
+
+
+def env_rank():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def init_comm(tg, group=None) -> None:
+    """Create the NCCL communicator of this TrackGenerator's context across the torch.distributed group."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    L = _lib.lib()
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        _lib.check(tg._ctx, L.rt_comm_unique_id(tg._ctx, buf))
+    t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    dist.broadcast(t, src=0, group=group)
+    ident = bytes(t.cpu().numpy().tobytes())
+    _lib.check(tg._ctx, L.rt_comm_init(tg._ctx, world, rank, ident))

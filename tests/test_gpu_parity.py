@@ -1,0 +1,286 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI
+(librt_b200.so via ctypes) and is compared with the CPU oracle on the same seeded inputs:
+track/segment counts, element ids and segment order bit-exact; p/q/len bit-exact (the bar in
+BASELINE.json is 1e-12 relative, the kernels are built to reproduce the reference's IEEE ops exactly);
+volumes to 1e-10 relative (atomics reorder the sum)."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import raytracing_jl_b200 as rt  # noqa: E402
+from oracle.oracle import OracleMesh, OracleTrackGenerator  # noqa: E402
+from tests.golden import runtests_goldens as G  # noqa: E402
+
+P_TOL = 1e-12  # relative tolerance named by BASELINE.json:north_star for p/q/len
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    rt.build()
+
+
+def bcs_of(codes):
+    t, b, r, l = (rt.BoundaryType(c) for c in codes)
+    return rt.BoundaryConditions(top=t, bottom=b, right=r, left=l)
+
+
+def run_both(model, n_azim, delta, bcs=(0, 0, 0, 0), flags=0, k=5, capacity=0):
+    mesh = rt.Mesh(model)
+    otg = OracleTrackGenerator(OracleMesh.from_mesh(mesh), n_azim, delta, bcs=bcs)
+    otg.trace()
+    otg.segmentize(k=k, check=False, nthreads=8)
+    tg = rt.TrackGenerator(mesh, n_azim, delta, bcs=bcs_of(bcs))
+    rt.trace_(tg)
+    if capacity:
+        from raytracing_jl_b200 import _lib
+        _lib.lib().rt_set_segment_capacity(tg._ctx, capacity)
+    rt.segmentize_(tg, k=k, flags=flags, check=False)
+    return otg, tg
+
+
+def assert_tracks_equal(otg, tg):
+    t, o = tg.track_data, otg.tracks
+    assert tg.n_total_tracks == otg.n_total_tracks
+    assert np.array_equal(tg.n_tracks_x, otg.n_tracks_x) and np.array_equal(tg.n_tracks_y, otg.n_tracks_y)
+    aq = tg.azimuthal_quadrature
+    assert np.array_equal(aq.phis, otg.phis) and np.array_equal(aq.deltas, otg.deltas) and np.array_equal(aq.weights, otg.weights)
+    for key in ("azim_idx", "track_idx", "bc_fwd", "bc_bwd", "dir_fwd", "dir_bwd", "next_fwd", "next_bwd"):
+        assert np.array_equal(t[key], o[key]), key
+    for key in ("p", "q", "phi", "len", "abc"):
+        assert np.array_equal(t[key], o[key]), key  # bit-exact
+
+
+def assert_segments_equal(otg, tg, whole=True):
+    assert tg.n_segments == otg.n_segments
+    assert np.array_equal(tg.segment_offsets, otg.seg_offsets)
+    assert np.array_equal(tg.segment_status, otg.seg_status)
+    assert (tg.first_bad_uid, tg.bad_status) == (otg.first_bad_uid, otg.bad_status)
+    if whole:
+        s, o = tg.segments, otg.seg
+        assert np.array_equal(s["element"], o["element"])
+        for key in ("px", "py", "qx", "qy", "len"):
+            assert np.array_equal(s[key], o[key]), key
+            scale = np.maximum(np.abs(o[key]), 1e-300)
+            assert (np.abs(s[key] - o[key]) / scale).max(initial=0.0) <= P_TOL
+
+
+def assert_volumes_close(otg, tg):
+    vo, vg = otg.volumes(), tg.volumes
+    assert np.abs(vg - vo).max() <= 1e-10 * np.abs(vo).max()
+
+
+# ---- trace! ------------------------------------------------------------------------------------------
+def test_trace_goldens_through_host_api(pincell_model):  # test/runtests.jl:10-27
+    tg = rt.TrackGenerator(pincell_model, G.MAIN["n_azim"], G.MAIN["delta"])
+    rt.trace_(tg)
+    assert tg.n_total_tracks == G.MAIN["n_total_tracks"]
+    assert tg.n_tracks_x.tolist() == G.MAIN["n_tracks_x"] and tg.n_tracks_y.tolist() == G.MAIN["n_tracks_y"]
+    assert tg.n_tracks.tolist() == G.MAIN["n_tracks"]
+    aq = tg.azimuthal_quadrature
+    assert (rt.nazim(aq), rt.nazim2(aq), rt.nazim4(aq)) == (8, 4, 2)
+    assert all(math.isclose(d, G.MAIN["delta_eff"], rel_tol=rt.RTOL_DEFAULT) for d in aq.deltas)
+    assert np.allclose(aq.phis, G.MAIN["phis"], rtol=rt.RTOL_DEFAULT, atol=0)
+
+
+@pytest.mark.parametrize("n_azim,table", [(4, G.LINKS_4), (8, G.LINKS_8)])
+def test_reflection_goldens_through_host_api(pincell_model, n_azim, table):  # test/runtests.jl:46-335
+    bcs = rt.BoundaryConditions(**{k: getattr(rt, v) for k, v in G.REFLECTION_BCS.items()})
+    tg = rt.TrackGenerator(pincell_model, n_azim, 0.8, bcs=bcs)
+    rt.trace_(tg)
+    for uid, (bf, bb, nf, nb, df, db) in table.items():
+        tr = tg.tracks_by_uid[uid]
+        assert int(rt.bc_fwd(tr)) == G.BC_CODE[bf] and int(rt.bc_bwd(tr)) == G.BC_CODE[bb]
+        assert tr.next_track_fwd.uid == nf and tr.next_track_bwd.uid == nb
+        assert int(rt.dir_next_track_fwd(tr)) == G.DIR_CODE[df] and int(rt.dir_next_track_bwd(tr)) == G.DIR_CODE[db]
+
+
+@pytest.mark.parametrize("n_azim,delta,bcs", [(8, 0.02, (0, 0, 0, 0)), (16, 0.08, (1, 1, 1, 1)), (32, 0.013, (2, 2, 2, 2)),
+                                             (4, 0.8, (0, 1, 0, 1)), (64, 0.05, (2, 1, 0, 2))])
+def test_trace_matches_oracle_bitwise(pincell_model, n_azim, delta, bcs):
+    mesh = rt.Mesh(pincell_model)
+    otg = OracleTrackGenerator(OracleMesh.from_mesh(mesh), n_azim, delta, bcs=bcs).trace()
+    tg = rt.TrackGenerator(mesh, n_azim, delta, bcs=bcs_of(bcs))
+    rt.trace_(tg)
+    assert_tracks_equal(otg, tg)
+
+
+# ---- segmentize! -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flags", [0, rt.RT_SEG_LITERAL])
+@pytest.mark.parametrize("n_azim,delta", [(8, 0.02), (16, 0.08), (32, 0.01), (4, 0.8)])
+def test_pincell_segments_match_oracle(pincell_model, n_azim, delta, flags):
+    otg, tg = run_both(pincell_model, n_azim, delta, flags=flags)
+    assert_tracks_equal(otg, tg)
+    assert_segments_equal(otg, tg)
+    assert_volumes_close(otg, tg)
+    assert otg.bad_status == 0
+
+
+def test_reference_invariants_on_gpu_result(pincell_model):  # test/runtests.jl:30-43
+    tg = rt.TrackGenerator(pincell_model, 8, 0.02)
+    rt.segmentize_(rt.trace_(tg))
+
+    def approx(a, b):
+        return np.linalg.norm(a - b) <= rt.RTOL_DEFAULT * max(np.linalg.norm(a), np.linalg.norm(b))
+
+    for track in tg.tracks_by_uid:
+        segs = track.segments
+        assert approx(track.p, segs[0].p) and approx(track.q, segs[-1].q)
+        assert math.isclose(track.ell, sum(rt.ell(s) for s in segs), rel_tol=rt.RTOL_DEFAULT)
+    assert math.isclose(tg.volumes.sum(), 2.56, rel_tol=1e-9)
+
+
+@pytest.mark.parametrize("seed,n,n_azim,delta", [(1234, 60, 16, 0.01), (7, 37, 32, 0.004), (99, 90, 8, 0.003)])
+def test_jittered_mesh_matches_oracle(seed, n, n_azim, delta):
+    model = rt.synth.jittered_triangle_mesh(n, n, seed=seed)
+    otg, tg = run_both(model, n_azim, delta)
+    assert_segments_equal(otg, tg)
+    assert_volumes_close(otg, tg)
+    st = tg.stats()
+    assert st["fast_transitions"] > 0.8 * tg.n_segments
+
+
+def test_offset_domain_and_rectangle():
+    """non-zero bb_min and a non-square domain (not covered by any reference test)"""
+    model = rt.synth.jittered_triangle_mesh(40, 25, lx=2.0, ly=1.25, seed=5, x0=-3.5, y0=10.0)
+    otg, tg = run_both(model, 16, 0.02, bcs=(1, 1, 1, 1))
+    assert_tracks_equal(otg, tg)
+    assert_segments_equal(otg, tg)
+
+
+def test_pin_lattice_matches_oracle():
+    model = rt.synth.pin_lattice_mesh(2, 1.26, 0.4096, 0.0655, 0.05, seed=3)
+    otg, tg = run_both(model, 32, 0.004, bcs=(1, 1, 1, 1))
+    assert_segments_equal(otg, tg)
+    assert_volumes_close(otg, tg)
+
+
+def test_cfg2_bwr_matches_oracle():
+    model, n_azim, delta = rt.synth.workload("cfg2")
+    otg, tg = run_both(model, n_azim, delta, bcs=(1, 1, 1, 1))
+    assert_segments_equal(otg, tg)
+    otg, tg = run_both(model, n_azim, 0.002, bcs=(1, 1, 1, 1))  # the delta test/bwr-gmsh.jl:151 itself uses
+    assert_segments_equal(otg, tg)
+
+
+def test_commensurate_boundary_vertex_hits(pincell_model):
+    """delta=0.08 makes every track start and end on a boundary mesh node: n_int=3 paths."""
+    otg, tg = run_both(pincell_model, 16, 0.08)
+    assert otg.stats()["n_int_ge3"] > 100
+    assert_segments_equal(otg, tg)
+
+
+def test_structured_mesh_exact_vertex_crossings():
+    """unjittered structured mesh: tracks through vertices / along edges, and error statuses must agree too"""
+    model = rt.synth.jittered_triangle_mesh(16, 16, jitter=0.0)
+    otg, tg = run_both(model, 8, 0.0625)
+    assert_segments_equal(otg, tg)
+
+
+def test_batched_fill_equals_single_shot(pincell_model):
+    otg, tg = run_both(pincell_model, 32, 0.01, capacity=20000)
+    assert tg.n_segments == otg.n_segments and np.array_equal(tg.segment_offsets, otg.seg_offsets)
+    # only the last batch is resident: compare it with the tail of the oracle's arrays
+    s = tg.segments
+    n = s["px"].shape[0]
+    assert 0 < n <= 20000
+    for key in ("px", "py", "qx", "qy", "len", "element"):
+        assert np.array_equal(s[key], otg.seg[key][-n:])
+    assert_volumes_close(otg, tg)
+    last = tg.tracks_by_uid[tg.n_total_tracks].segments
+    assert len(last) == otg.seg_counts[-1]
+
+
+def test_idempotent_and_max_iter(pincell_model):
+    tg = rt.TrackGenerator(pincell_model, 8, 0.05)
+    rt.segmentize_(rt.trace_(tg))
+    a = {k: v.copy() for k, v in tg.segments.items()}
+    v0 = tg.volumes.copy()
+    rt.segmentize_(tg)
+    assert all(np.array_equal(a[k], tg.segments[k]) for k in a)
+    assert np.abs(tg.volumes - v0).max() <= 1e-12
+    # MAX_ITER cap (src/track.jl:104,119): tracks stop at max_iter segments and fail the length check
+    rt.segmentize_(tg, max_iter=10, check=False)
+    assert np.diff(tg.segment_offsets).max() == 10 and tg.bad_status == 2
+
+
+def test_error_paths(pincell_model):
+    tg = rt.TrackGenerator(pincell_model, 8, 0.05)
+    with pytest.raises(RuntimeError):
+        rt.segmentize_(tg)  # src/trackgenerator.jl:360-361
+    for args in [(0, 0.1), (6, 0.1), (8, 0.0)]:
+        with pytest.raises(rt.DomainError):
+            rt.TrackGenerator(pincell_model, *args)
+
+
+def test_neighbour_table(pincell_model):
+    tg = rt.TrackGenerator(pincell_model, 4, 0.8)
+    nb = tg.neighbours()
+    tri = pincell_model.triangles0()
+    edges = {}
+    for c, t in enumerate(tri):
+        for k in range(3):
+            edges.setdefault(frozenset((t[k], t[(k + 1) % 3])), []).append(c)
+    for c, t in enumerate(tri):
+        for k in range(3):
+            cs = [x for x in edges[frozenset((t[k], t[(k + 1) % 3]))] if x != c]
+            assert nb[c, k] == (cs[0] + 1 if cs else 0)
+
+
+def test_shard_planner_matches_device(pincell_model):
+    from raytracing_jl_b200 import _lib
+    from raytracing_jl_b200.api import _angle_tables
+    from raytracing_jl_b200.distributed import plan_shards
+
+    tg = rt.TrackGenerator(pincell_model, 32, 0.01)
+    _, _, tan_t, dxe, dye = _angle_tables(tg)
+    for parts in (2, 3, 8):
+        host = plan_shards(tg, parts)
+        dev = np.zeros(parts + 1, np.int64)
+        _lib.check(tg._ctx, _lib.lib().rt_plan_shards(tg._ctx, 16, tg.n_tracks_x, tg.n_tracks_y, tg.azimuthal_quadrature.phis,
+                                                      tan_t, dxe, dye, parts, dev))
+        assert dev[0] == 1 and dev[-1] == tg.n_total_tracks + 1
+        assert np.abs(dev - host).max() <= 1  # summation order may move a split by one track
+
+
+def test_sharded_union_equals_whole(pincell_model):
+    """uid-range shards on one GPU: the union of the shards' segments is the single-context result"""
+    whole = rt.TrackGenerator(pincell_model, 16, 0.02, bcs=bcs_of((1, 1, 1, 1)))
+    rt.segmentize_(rt.trace_(whole))
+    parts, vol = [], np.zeros_like(whole.volumes)
+    for r in range(3):
+        tg = rt.TrackGenerator(pincell_model, 16, 0.02, bcs=bcs_of((1, 1, 1, 1)), shard=(r, 3))
+        rt.segmentize_(rt.trace_(tg))
+        parts.append(tg)
+        vol += tg.volumes
+    assert parts[0].uid_begin == 1 and parts[-1].uid_end == whole.n_total_tracks + 1
+    for key in ("px", "py", "qx", "qy", "len", "element"):
+        assert np.array_equal(np.concatenate([p.segments[key] for p in parts]), whole.segments[key])
+    assert np.abs(vol - whole.volumes).max() <= 1e-12
+    assert np.array_equal(np.concatenate([p.track_data["next_fwd"] for p in parts]), whole.track_data["next_fwd"])
+
+
+# ---- size-independent properties at a larger size -------------------------------------------------------
+def test_properties_at_scale():
+    model, n_azim, delta = rt.synth.workload("cfg3", scale=0.25)  # ~250 k triangles
+    tg = rt.TrackGenerator(model, n_azim, 4 * delta, bcs=bcs_of((1, 1, 1, 1)))
+    rt.segmentize_(rt.trace_(tg), check=False)
+    off, s, t = tg.segment_offsets, tg.segments, tg.track_data
+    ok = tg.segment_status == 0
+    assert ok.mean() > 0.999
+    seg_sum = np.add.reduceat(s["len"], off[:-1])
+    assert np.all(np.abs(seg_sum[ok] - t["len"][ok]) <= rt.RTOL_DEFAULT * t["len"][ok])
+    # contiguity q_k == p_{k+1} inside a track (bit-identical on generic transitions, close otherwise)
+    inner = np.ones(s["px"].shape[0], bool)
+    inner[off[1:-1]] = False
+    d = np.hypot(s["qx"][:-1] - s["px"][1:], s["qy"][:-1] - s["py"][1:])[inner[1:]]
+    assert d.max() < 1e-6 and (d == 0).mean() > 0.99
+    assert s["element"].min() >= 1 and s["element"].max() <= model.num_cells
+    assert math.isclose(tg.volumes.sum(), 1.0, rel_tol=1e-6)
+    # idempotence of the checksum
+    chk = (float(s["len"].sum()), int(s["element"].astype(np.int64).sum()))
+    rt.segmentize_(tg, check=False)
+    s2 = tg.segments
+    assert chk == (float(s2["len"].sum()), int(s2["element"].astype(np.int64).sum()))
