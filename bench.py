@@ -1,0 +1,274 @@
+#!/usr/bin/env python
+"""bench.py -- segments/s of segmentize! (BASELINE.json:metric) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg2|cfg4|cfg5|pincell] [--impl ours|reference]
+
+A "step" is one pass of the hot path over the workload's tracks with mesh + tracks already resident in
+HBM: count pass -> scan -> fill pass (+ fused per-element volumes) -> volumes normalise (+ NCCL all-reduce
+when N > 1).  The default workload is BASELINE.json configs[2] (unit square, ~1.0 M jittered triangles,
+n_phi = 64, delta = 1e-3), the largest named configuration whose 2.2 GB of segments fit one GPU without
+batching.  For N > 1 the tracks are sharded by uid range (mesh replicated) and the track spacing is
+delta / N, so per-GPU work stays fixed ("scaling": "weak").  `e2e` is the same metric through the host API
+with HOST buffers: mesh upload (H2D) + trace! + segmentize! + download of every Segment record (D2H).
+`--impl reference` times the reference's CPU algorithm (the oracle port: Julia is not installable here)
+on all host cores over a bounded uid sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def load_workload(name, n_gpus):
+    import raytracing_jl_b200 as rt
+
+    if name == "pincell":
+        d = np.load(os.path.join(ROOT, "tests", "golden", "pincell.npz"))
+        model, n_azim, delta = rt.UnstructuredDiscreteModel(d["node_coordinates"], d["cell_ptrs"], d["cell_data"]), 8, 2e-2
+    else:
+        model, n_azim, delta = rt.synth.workload(name)
+    return model, n_azim, delta / n_gpus
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_sample(model, n_azim, delta, budget_segments=3.0e7, blocks=16, threads=None):
+    """Reference CPU algorithm (oracle port) over `blocks` uid ranges spread evenly over the workload."""
+    import raytracing_jl_b200 as rt
+    from oracle.oracle import OracleMesh, OracleTrackGenerator
+
+    threads = threads or os.cpu_count() or 1
+    mesh = rt.Mesh(model)
+    otg = OracleTrackGenerator(OracleMesh.from_mesh(mesh), n_azim, delta, bcs=(1, 1, 1, 1)).trace()
+    n = otg.n_total_tracks
+    est_total = (mesh.width * mesh.height) * (n_azim / 2) / delta / (0.45 * (2 * mesh.width * mesh.height / model.num_cells) ** 0.5)
+    frac = min(1.0, budget_segments / max(est_total, 1.0))
+    per = max(1, int(n * frac / blocks))
+    segs, secs = 0, 0.0
+    for b in range(blocks):
+        u0 = 1 + int(b * (n - per) / max(blocks - 1, 1)) if frac < 1.0 else 1 + b * (n // blocks)
+        u1 = u0 + per if frac < 1.0 else (n + 1 if b == blocks - 1 else 1 + (b + 1) * (n // blocks))
+        t0 = time.perf_counter()
+        otg.segmentize(uid_begin=u0, uid_end=u1, nthreads=threads, fetch=False, check=False)
+        secs += time.perf_counter() - t0
+        segs += otg.n_segments
+        otg.free_segments()
+    return segs, secs, threads, f"{blocks} uid blocks x {per} tracks = {100 * min(1.0, blocks * per / n):.1f}% of {n} tracks"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    model, n_azim, delta = load_workload(args.workload, args.gpus)
+    threads = os.cpu_count() or 1
+    budget = 2.0e7 / max(1, args.steps + args.warmup) * 3
+    tot_s, tot_t, sample = 0, 0.0, ""
+    for it in range(args.warmup + args.steps):
+        s, t, threads, sample = cpu_sample(model, n_azim, delta, budget_segments=budget, threads=threads)
+        if it >= args.warmup:
+            tot_s += s
+            tot_t += t
+    v = tot_s / tot_t
+    out = {"impl": "reference", "metric": "segments/sec for segmentize!", "value": v, "unit": "segments/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": workload_config(args, model, n_azim, delta),
+           "cpu_baseline": {"value": v, "unit": "segments/s", "cores": threads, "kind": "port",
+                            "sample": sample + " per step; OpenMP over tracks (the reference itself is serial)"},
+           "e2e": {"value": v, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def workload_config(args, model, n_azim, delta):
+    names = {"cfg3": "BASELINE.json configs[2]: synthetic unit-square jittered triangular mesh, seed 1234",
+             "cfg2": "BASELINE.json configs[1]: synthetic 4x4 BWR pin lattice", "pincell": "BASELINE.json configs[0]: demo/pincell",
+             "cfg4": "BASELINE.json configs[3]: synthetic 17x17 pin lattice", "cfg5": "BASELINE.json configs[4]: synthetic 51x51 pin lattice"}
+    return {"workload": names.get(args.workload, args.workload), "n_cells": int(model.num_cells), "n_nodes": int(model.num_nodes),
+            "n_azim": n_azim, "delta": delta, "bcs": "reflective", "sharding": f"uid ranges over {args.gpus} GPU(s), mesh replicated",
+            "l2": "inputs larger than L2: cell+edge records 160 B/cell and >2 GB of segment output stream through the 126 MB L2 every step"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="cfg3")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import raytracing_jl_b200 as rt
+    from raytracing_jl_b200 import _lib
+    from raytracing_jl_b200.distributed import init_comm
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rt.build()
+    model, n_azim, delta = load_workload(args.workload, world)
+    mesh = rt.Mesh(model)
+    bcs = rt.BoundaryConditions(top=rt.Reflective, bottom=rt.Reflective, right=rt.Reflective, left=rt.Reflective)
+    tg = rt.TrackGenerator(mesh, n_azim, delta, bcs=bcs, device=local, shard=(rank, world))
+    if world > 1:
+        init_comm(tg)
+    rt.trace_(tg)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        rt.segmentize_(tg, check=False, fetch_volumes=False)
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    tg.timer_start()
+    phases = []
+    for _ in range(args.steps):
+        step()
+        phases.append(tg.phase_ms())
+    ms = tg.timer_stop()
+    barrier()
+    clocks = sampler.stop()
+    nseg_local = tg.n_segments
+    st = tg.stats()
+    t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    n_all = torch.tensor([float(nseg_local), float(tg.uid_end - tg.uid_begin)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n_all, op=dist.ReduceOp.SUM)
+    ms_max = float(t_ms.item())
+    nseg, ntrk = float(n_all[0].item()), float(n_all[1].item())
+    value = nseg * args.steps / (ms_max * 1e-3)
+
+    # ---- roofline of the dominant kernel (the fill pass k_walk<true>): SURVEY 8(d) algorithmic bytes per launch
+    fill_ms = float(np.mean([p["fill"] for p in phases]))
+    count_ms = float(np.mean([p["count"] for p in phases]))
+    alg_bytes = 44.0 * nseg_local + 72.0 * (tg.uid_end - tg.uid_begin) + 40.0 * model.num_cells
+    peak, peak_src = peaks()
+    achieved = alg_bytes / (fill_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_walk<true> (fill pass)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                "launch_ms": fill_ms, "count_pass_ms": count_ms,
+                "note": "FP64 walk is latency/ALU bound, not HBM bound; see DESIGN.md and profiles/"}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get(args.workload)
+        except Exception:
+            pass
+
+    # ---- e2e through the public API with host buffers
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            tg.upload_mesh()  # H2D of the flattened model + device preparation
+            rt.trace_(tg)
+            rt.segmentize_(tg, check=False)  # includes the D2H of volumes
+            tg.segment_offsets
+            return tg.fetch_segments(pinned=True)  # D2H of every Segment record into pinned host buffers
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = 2
+        for _ in range(n_e2e):
+            seg = e2e_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        h2d = tg.mesh_h2d_bytes() + 7 * 8 * n_azim // 2
+        d2h = sum(v.nbytes for v in seg.values()) + tg.segment_offsets.nbytes + tg.segment_status.nbytes + tg.volumes.nbytes
+        e2e = {"value": nseg * n_e2e / float(dt.item()), "unit": "segments/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(dt.item()) / n_e2e,
+               "what": "rt_mesh_upload + rt_trace + rt_segmentize + rt_volumes + rt_segment_offsets + rt_segments_download"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        s, t, cores, sample = cpu_sample(model, n_azim, delta)
+        cpu = {"value": s / t, "unit": "segments/s", "cores": cores, "kind": "port", "sample": sample,
+               "note": "oracle port of the reference algorithm, OpenMP over tracks; the Julia reference itself is single-threaded"}
+
+    if rank == 0:
+        out = {"metric": "segments/sec for segmentize!", "value": value, "unit": "segments/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, model, n_azim, delta),
+               "segments_per_step": nseg, "tracks": ntrk, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+               "gpu_launches": int(st["launches"] + 1) * args.steps,
+               "phase_ms": {k: float(np.mean([p[k] for p in phases])) for k in phases[0]},
+               "walk_stats": {k: st[k] for k in ("fast_transitions", "literal_iterations", "nn_queries", "knn_queries")},
+               "bad_tracks_status": int(tg.bad_status)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

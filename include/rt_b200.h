@@ -154,6 +154,10 @@ int rt_stats(rt_ctx *ctx, double stats[8]);
  * 3 scan, 4 fill, 5 volumes(+allreduce) */
 int rt_phase_ms(rt_ctx *ctx, double ms[6]);
 
+/* CUDA-event stopwatch on the context's launching stream (bench harness: torch.cuda.Event cannot see it). */
+int rt_timer_start(rt_ctx *ctx);
+int rt_timer_stop(rt_ctx *ctx, double *elapsed_ms);
+
 #ifdef __cplusplus
 }
 #endif

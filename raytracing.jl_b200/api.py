@@ -287,9 +287,28 @@ class TrackGenerator:
         if rc:
             raise _lib.RTError(rc, f"rt_create(device={device}) failed: no usable CUDA device (there is no CPU fallback)")
         self._ctx = h
-        m = mesh.model
-        _lib.check(h, L.rt_mesh_upload(h, m.num_nodes, m.node_coordinates.reshape(-1), m.num_cells, mesh.cell_nodes[0],
-                                       mesh.cell_nodes[1], mesh.node_cells[0], mesh.node_cells[1], mesh.bb_min, mesh.bb_max))
+        self.upload_mesh()
+
+    def upload_mesh(self):
+        """Host -> device copy of the flattened mesh + device-side preparation (rt_mesh_upload)."""
+        mesh, m = self.mesh, self.mesh.model
+        _lib.check(self._ctx, _lib.lib().rt_mesh_upload(
+            self._ctx, m.num_nodes, m.node_coordinates.reshape(-1), m.num_cells, mesh.cell_nodes[0], mesh.cell_nodes[1],
+            mesh.node_cells[0], mesh.node_cells[1], mesh.bb_min, mesh.bb_max))
+        self._traced = self._segmented = False
+        self._track_data = self._segments = self._offsets = None
+
+    def mesh_h2d_bytes(self) -> int:
+        mesh, m = self.mesh, self.mesh.model
+        return int(m.node_coordinates.nbytes + sum(a.nbytes for a in mesh.cell_nodes) + sum(a.nbytes for a in mesh.node_cells))
+
+    def timer_start(self):
+        _lib.check(self._ctx, _lib.lib().rt_timer_start(self._ctx))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double(0.0)
+        _lib.check(self._ctx, _lib.lib().rt_timer_stop(self._ctx, C.byref(ms)))
+        return ms.value
 
     # ---- lazily fetched device results -------------------------------------------------------------
     @property
@@ -441,7 +460,7 @@ def trace_(tg: TrackGenerator) -> TrackGenerator:
 
 
 def segmentize_(tg: TrackGenerator, k: int = 5, rtol: float = RTOL_DEFAULT, flags: int = 0, max_iter: int = MAX_ITER,
-                check: bool = True) -> TrackGenerator:
+                check: bool = True, fetch_volumes: bool = True) -> TrackGenerator:
     """segmentize!(tg; k, rtol): count pass -> scan -> fill pass (+ fused fill_volumes) on the device."""
     L = _lib.lib()
     if not tg._traced:
@@ -462,5 +481,5 @@ def segmentize_(tg: TrackGenerator, k: int = 5, rtol: float = RTOL_DEFAULT, flag
         _lib.check(tg._ctx, rc)
         tg._segmented = True
     if not (flags & _lib.RT_SEG_NO_VOLUMES):
-        _lib.check(tg._ctx, L.rt_volumes(tg._ctx, _lib.ptr(tg.volumes)))
+        _lib.check(tg._ctx, L.rt_volumes(tg._ctx, _lib.ptr(tg.volumes) if fetch_volumes else None))
     return tg

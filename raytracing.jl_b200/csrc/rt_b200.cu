@@ -44,6 +44,7 @@ struct rt_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaEvent_t tev[2] = {nullptr, nullptr};
 
     // mesh
     bool has_mesh = false;
@@ -147,7 +148,8 @@ extern "C" int rt_create(rt_ctx **out, int device) {
     rt_ctx *ctx = new rt_ctx();
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&ctx->ev[0]) != cudaSuccess || cudaEventCreate(&ctx->ev[1]) != cudaSuccess) {
+        cudaEventCreate(&ctx->ev[0]) != cudaSuccess || cudaEventCreate(&ctx->ev[1]) != cudaSuccess ||
+        cudaEventCreate(&ctx->tev[0]) != cudaSuccess || cudaEventCreate(&ctx->tev[1]) != cudaSuccess) {
         delete ctx;
         return RT_ERR_CUDA;
     }
@@ -872,5 +874,23 @@ extern "C" int rt_stats(rt_ctx *ctx, double stats[8]) {
 extern "C" int rt_phase_ms(rt_ctx *ctx, double ms[6]) {
     if (!ctx || !ms) return RT_ERR_ARG;
     memcpy(ms, ctx->phase_ms, sizeof(ctx->phase_ms));
+    return RT_OK;
+}
+
+extern "C" int rt_timer_start(rt_ctx *ctx) {
+    if (!ctx) return RT_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventRecord(ctx->tev[0], ctx->stream));
+    return RT_OK;
+}
+
+extern "C" int rt_timer_stop(rt_ctx *ctx, double *elapsed_ms) {
+    if (!ctx || !elapsed_ms) return RT_ERR_ARG;
+    CK(cudaEventRecord(ctx->tev[1], ctx->stream));
+    CK(cudaEventSynchronize(ctx->tev[1]));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->tev[0], ctx->tev[1]));
+    *elapsed_ms = (double)ms;
     return RT_OK;
 }
