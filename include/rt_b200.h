@@ -55,7 +55,8 @@ enum {
     RT_SEG_DEFAULT = 0,
     RT_SEG_LITERAL = 1,     /* disable the adjacency fast path: every step re-locates like src/track.jl:122 */
     RT_SEG_NO_VOLUMES = 2,  /* skip the fused fill_volumes accumulation */
-    RT_SEG_COUNT_ONLY = 4   /* count + scan only (no segment buffers are written) */
+    RT_SEG_COUNT_ONLY = 4,  /* count + scan only (no segment buffers are written) */
+    RT_SEG_NO_CHUNKS = 8    /* one walker per track (no sub-track chunks) */
 };
 
 /* ---- context ------------------------------------------------------------------------------------- */
@@ -154,6 +155,9 @@ int rt_stats(rt_ctx *ctx, double stats[8]);
  * 3 scan, 4 fill, 5 volumes(+allreduce) */
 int rt_phase_ms(rt_ctx *ctx, double ms[6]);
 
+/* tuning knobs: "chunk_segments" (minimum expected segments per sub-track chunk, default 64),
+ * "target_walkers" (chunks are sized so that about this many walkers exist, default 148*2048*4) */
+int rt_set_option(rt_ctx *ctx, const char *name, double value);
 /* CUDA-event stopwatch on the context's launching stream (bench harness: torch.cuda.Event cannot see it). */
 int rt_timer_start(rt_ctx *ctx);
 int rt_timer_stop(rt_ctx *ctx, double *elapsed_ms);

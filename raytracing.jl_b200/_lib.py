@@ -81,11 +81,12 @@ SYMBOLS = {
     "rt_comm_init": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_char_p]),
     "rt_stats": (C.c_int, [_vp, _f64]),
     "rt_phase_ms": (C.c_int, [_vp, _f64]),
+    "rt_set_option": (C.c_int, [_vp, C.c_char_p, C.c_double]),
     "rt_timer_start": (C.c_int, [_vp]),
     "rt_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_double)]),
 }
 
-RT_SEG_LITERAL, RT_SEG_NO_VOLUMES, RT_SEG_COUNT_ONLY = 1, 2, 4
+RT_SEG_LITERAL, RT_SEG_NO_VOLUMES, RT_SEG_COUNT_ONLY, RT_SEG_NO_CHUNKS = 1, 2, 4, 8
 
 _lib = None
 

@@ -302,6 +302,9 @@ class TrackGenerator:
         mesh, m = self.mesh, self.mesh.model
         return int(m.node_coordinates.nbytes + sum(a.nbytes for a in mesh.cell_nodes) + sum(a.nbytes for a in mesh.node_cells))
 
+    def set_option(self, name: str, value: float):
+        _lib.check(self._ctx, _lib.lib().rt_set_option(self._ctx, name.encode(), float(value)))
+
     def timer_start(self):
         _lib.check(self._ctx, _lib.lib().rt_timer_start(self._ctx))
 

@@ -65,8 +65,10 @@ __global__ void k_neighbours(int n_cells, const int *cell_nodes, const int *nc_p
 }
 
 struct MeshScalars {
-    double lmax;  // longest edge
-    double smax;  // largest |coordinate|
+    double lmax;      // longest edge
+    double smax;      // largest |coordinate|
+    double edge_sum;  // sum over (cell, edge) of the edge length (interior edges counted twice)
+    double area;      // total mesh area
 };
 
 __device__ __forceinline__ void atomic_max_double(double *addr, double v) {
@@ -80,7 +82,8 @@ __device__ __forceinline__ void atomic_max_double(double *addr, double v) {
 __global__ void k_cell_records(DevMesh m, const int *nbr, CellRec *cells, EdgeRec *edges, float *qual, float *bdist,
                                MeshScalars *sc) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= m.n_cells) return;
+    const bool live = c < m.n_cells;
+    if (!live) c = m.n_cells - 1;  // keep the warp converged for the reductions below; results are not stored
     P2 v[3];
     for (int k = 0; k < 3; ++k) {
         double2 p = m.xy[m.cell_nodes[3 * c + k]];
@@ -101,7 +104,7 @@ __global__ void k_cell_records(DevMesh m, const int *nbr, CellRec *cells, EdgeRe
         e.b = l.b;
         e.c = l.c;
         e.len = norm2(v[k].x - v[j].x, v[k].y - v[j].y);
-        edges[3 * c + k] = e;
+        if (live) edges[3 * c + k] = e;
         len[k] = e.len;
         lmax = fmax(lmax, e.len);
         smax = fmax(smax, fmax(fabs(v[k].x), fabs(v[k].y)));
@@ -114,17 +117,33 @@ __global__ void k_cell_records(DevMesh m, const int *nbr, CellRec *cells, EdgeRe
     double sigma = fmin(s0, fmin(s1, s2));
     double hmin = area2 / lmax;
     r.clear = INFINITY;
-    cells[c] = r;
-    qual[c] = (sigma > 0.0 && hmin > 0.0) ? (float)(1.0 / sigma) : INFINITY;
-    bdist[c] = (float)bd;
+    if (live) {
+        cells[c] = r;
+        qual[c] = (sigma > 0.0 && hmin > 0.0) ? (float)(1.0 / sigma) : INFINITY;
+        bdist[c] = (float)bd;
+    } else {
+        len[0] = len[1] = len[2] = 0.0;
+        area2 = 0.0;
+    }
     // hmin feeds the lambda rounding-error term; stash via a second pass using smax (global), see k_finalize_clear
     atomic_max_double(&sc->lmax, lmax);
     atomic_max_double(&sc->smax, smax);
+    // Cauchy-Crofton: a random line crosses edge_sum / (pi * area) cell edges per unit length (chunk sizing only)
+    double es = len[0] + len[1] + len[2], ar = 0.5 * area2;
+    for (int o = 16; o > 0; o >>= 1) {
+        es += __shfl_down_sync(0xffffffffu, es, o);
+        ar += __shfl_down_sync(0xffffffffu, ar, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sc->edge_sum, es);
+        atomicAdd(&sc->area, ar);
+    }
 }
 
 // clear[c] for one (tiny_step) value; see DESIGN.md "fast-path equivalence" for the derivation.
 //   reach R = (8*rtol + 64*eps*(S/hmin_c)^2) * Lmax      (how far outside a cell its tolerant test can pass)
-//   clear_c = 16 * (R + tiny) / sigma_c                     (+inf for cells touching the bounding box band)
+//   clear_c = 8 * R / sigma_c ; stored NEGATIVE for cells with a vertex inside the bounding-box band (the fast path
+//   then also checks that the re-location points are not `inboundary`), +inf for degenerate cells (always literal)
 __global__ void k_finalize_clear(DevMesh m, CellRec *cells, const float *qual, const float *bdist, const MeshScalars *sc,
                                  double tiny) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -136,11 +155,14 @@ __global__ void k_finalize_clear(DevMesh m, CellRec *cells, const float *qual, c
     double hmin = area2 / lmax;
     double ratio = sc->smax / hmin;
     double reach = (8.0 * kRtol + 64.0 * 2.220446049250313e-16 * ratio * ratio) * sc->lmax;
-    double clear = 16.0 * (reach + tiny) * (double)qual[c] * 1.001;
-    bool boundary = !((double)bdist[c] > 8.0 * tiny + 1e-12 * sc->smax);
+    double clear = 8.0 * reach * (double)qual[c] * 1.001;
+    bool boundary = !((double)bdist[c] > 16.0 * tiny + 1e-12 * sc->smax);
     float cf = (float)clear;
     if (!(cf >= clear)) cf = nextafterf(cf, INFINITY);
-    if (boundary || !isfinite(clear) || !(hmin > 0.0)) cf = INFINITY;
+    if (!isfinite(clear) || !(hmin > 0.0))
+        cf = INFINITY;
+    else if (boundary)
+        cf = -cf;
     cells[c].clear = cf;
 }
 

@@ -71,6 +71,12 @@ struct rt_ctx {
     // segmentation
     bool segmented = false;
     DevBuf b_count, b_status, b_offsets, b_tile, b_vol, b_voln, b_counters, b_bad;
+    DevBuf b_nch, b_blk_chunks, b_unit_base, b_unit_block, b_ch_i, b_ch_d;  // chunk plan (walk.cuh ChunkPlan)
+    long long n_units = 0;
+    double opt_chunk_segments = 64.0;               // minimum expected segments per chunk
+    double opt_target_walkers = 148.0 * 2048.0 * 4.0;  // chunks are sized so that about this many walkers exist
+    double sum_len = 0.0;              // total track length of the shard
+    double edge_sum = 0.0, area = 0.0;  // mesh density scalars (chunk sizing)
     long long total_segments = 0;
     long long cap_cfg = 0;  // user limit on resident segments (0 = as many as fit)
     long long cap = 0;      // allocated
@@ -165,7 +171,8 @@ extern "C" void rt_destroy(rt_ctx *ctx) {
                      &ctx->b_edges,   &ctx->b_qual,       &ctx->b_bdist,    &ctx->b_sc,      &ctx->b_grid_ptrs, &ctx->b_grid_nodes,
                      &ctx->b_ang_d,   &ctx->b_ang_i,      &ctx->b_trk_d,    &ctx->b_trk_i,   &ctx->b_trk_l,   &ctx->b_trk_c,
                      &ctx->b_err,     &ctx->b_count,      &ctx->b_status,   &ctx->b_offsets, &ctx->b_tile,    &ctx->b_vol,
-                     &ctx->b_voln,    &ctx->b_counters,   &ctx->b_bad,      &ctx->b_seg_d,   &ctx->b_seg_e};
+                     &ctx->b_voln,    &ctx->b_counters,   &ctx->b_bad,      &ctx->b_seg_d,   &ctx->b_seg_e,
+                     &ctx->b_nch,     &ctx->b_blk_chunks, &ctx->b_unit_base, &ctx->b_unit_block, &ctx->b_ch_i, &ctx->b_ch_d};
     for (DevBuf *b : all) release(*b);
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
     if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
@@ -286,6 +293,8 @@ extern "C" int rt_mesh_upload(rt_ctx *ctx, int32_t n_nodes, const double *xy, in
     release(cursor);
     ctx->smax = sc.smax;
     ctx->lmax = sc.lmax;
+    ctx->edge_sum = sc.edge_sum;
+    ctx->area = sc.area;
     ctx->clear_tiny = -1.0;
     ctx->has_mesh = true;
     ctx->traced = false;
@@ -408,12 +417,20 @@ extern "C" int rt_trace(rt_ctx *ctx, int32_t n_azim_2, const int64_t *n_tracks_x
     P.n = n;
     P.t = t;
     tic(ctx);
-    if (n > 0) k_trace<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(P);
+    DevBuf dsum;
+    CK(ensure(dsum, sizeof(double)));
+    CK(cudaMemsetAsync(dsum.p, 0, sizeof(double), ctx->stream));
+    if (n > 0) {
+        k_trace<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(P);
+        k_sum_double<<<std::min(1024u, blocks_for(n, 256)), 256, 0, ctx->stream>>>(t.len, n, (double *)dsum.p);
+    }
     CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&ctx->sum_len, dsum.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     unsigned long long err = 0;
     CK(cudaMemcpyAsync(&err, ctx->b_err.p, sizeof(err), cudaMemcpyDeviceToHost, ctx->stream));
     ctx->phase_ms[1] = toc(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
+    release(dsum);
     if (err != ~0ULL) {
         long long uid = (long long)(err >> 4);
         int code = (int)(err & 15);
@@ -646,14 +663,59 @@ extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rt
     const bool count_only = (flags & RT_SEG_COUNT_ONLY) != 0;
     double launches = 0;
 
-    // ---- count pass
+    // ---- chunk plan: cut tracks so that ~target_walkers independent walkers exist, >= 64 segments each
     tic(ctx);
-    P.trk_begin = 0;
     P.n_tracks = n;
-    P.vol = (want_vol && count_only) ? (double *)ctx->b_vol.p : nullptr;
+    P.trk_begin = 0;
+    P.trk_end = n;
+    std::vector<long long> h_unit_base;
     if (n > 0) {
-        k_walk<false><<<blocks_for(n, 128), 128, 0, st>>>(P);
-        launches += 1;
+        const long long n_blocks = (n + 31) / 32;
+        double rho = ctx->edge_sum / (kPi * ctx->area);  // expected cell crossings per unit track length
+        double est_total = ctx->sum_len * rho;
+        double seg_target = fmax(ctx->opt_chunk_segments, est_total / ctx->opt_target_walkers);
+        double chunk_len = (flags & RT_SEG_NO_CHUNKS) || !(rho > 0.0) ? INFINITY : seg_target / rho;
+        CK(ensure(ctx->b_nch, sizeof(int) * (size_t)n));
+        CK(ensure(ctx->b_blk_chunks, sizeof(int) * (size_t)n_blocks));
+        CK(ensure(ctx->b_unit_base, sizeof(long long) * ((size_t)n_blocks + 1)));
+        k_plan_chunks<<<blocks_for(n_blocks * 32, 128), 128, 0, st>>>(n, ctx->t.len, chunk_len, (int *)ctx->b_nch.p,
+                                                                     (int *)ctx->b_blk_chunks.p);
+        CK((exclusive_scan<int, long long>(ctx, (const int *)ctx->b_blk_chunks.p, (long long *)ctx->b_unit_base.p, n_blocks)));
+        long long n_units = 0;
+        CK(cudaMemcpyAsync(&n_units, (long long *)ctx->b_unit_base.p + n_blocks, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        size_t nc = (size_t)n_units * 32;
+        CK(ensure(ctx->b_unit_block, sizeof(int) * (size_t)n_units));
+        CK(ensure(ctx->b_ch_i, sizeof(int) * 5 * nc));
+        CK(ensure(ctx->b_ch_d, sizeof(double) * 3 * nc));
+        k_fill_units<<<blocks_for(n_blocks, 128), 128, 0, st>>>(n_blocks, (const long long *)ctx->b_unit_base.p,
+                                                                 (int *)ctx->b_unit_block.p);
+        ChunkPlan &ch = P.ch;
+        ch.nch = (int *)ctx->b_nch.p;
+        ch.unit_block = (int *)ctx->b_unit_block.p;
+        ch.unit_base = (long long *)ctx->b_unit_base.p;
+        ch.n_units = n_units;
+        int *ci = (int *)ctx->b_ch_i.p;
+        ch.seed_cell = ci;
+        ch.seed_kexit = ci + nc;
+        ch.count = ci + 2 * nc;
+        ch.endcode = ci + 3 * nc;
+        ch.prefix = ci + 4 * nc;
+        double *cd = (double *)ctx->b_ch_d.p;
+        ch.seed_qx = cd;
+        ch.seed_qy = cd + nc;
+        ch.sum = cd + 2 * nc;
+        P.unit_begin = 0;
+        P.unit_end = n_units;
+        ctx->n_units = n_units;
+        launches += 5;
+        // ---- seeds, count pass, per-track fix-up
+        P.vol = nullptr;
+        k_seed<<<blocks_for(n_units * 32, 128), 128, 0, st>>>(P);
+        P.vol = (want_vol && count_only) ? (double *)ctx->b_vol.p : nullptr;
+        k_walk<false><<<blocks_for(n_units * 32, 128), 128, 0, st>>>(P);
+        k_fixup_tracks<<<blocks_for(n, 128), 128, 0, st>>>(P);
+        launches += 3;
     }
     CK(cudaGetLastError());
     ctx->phase_ms[2] = toc(ctx);
@@ -701,6 +763,8 @@ extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rt
         if (total > cap) {
             h_off.resize((size_t)n + 1);
             CK(cudaMemcpy(h_off.data(), ctx->b_offsets.p, sizeof(long long) * ((size_t)n + 1), cudaMemcpyDeviceToHost));
+            h_unit_base.resize((size_t)((n + 31) / 32) + 1);
+            CK(cudaMemcpy(h_unit_base.data(), ctx->b_unit_base.p, sizeof(long long) * h_unit_base.size(), cudaMemcpyDeviceToHost));
         }
         tic(ctx);
         long long b = 0;
@@ -713,9 +777,13 @@ extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rt
                 if (e <= b) return fail(ctx, RT_ERR_NOMEM, "rt_segmentize: one track needs more than the segment capacity");
             }
             P.trk_begin = b;
-            P.n_tracks = e - b;
+            P.trk_end = e;
             P.offset_base = total > cap ? h_off[b] : 0;
-            k_walk<true><<<blocks_for(e - b, 128), 128, 0, st>>>(P);
+            if (total > cap) {  // the warp units of the 32-track blocks overlapping [b, e)
+                P.unit_begin = h_unit_base[(size_t)(b >> 5)];
+                P.unit_end = h_unit_base[(size_t)((e - 1) >> 5) + 1];
+            }
+            k_walk<true><<<blocks_for((P.unit_end - P.unit_begin) * 32, 128), 128, 0, st>>>(P);
             launches += 1;
             CK(cudaGetLastError());
             ctx->res_trk_begin = b;
@@ -892,5 +960,17 @@ extern "C" int rt_timer_stop(rt_ctx *ctx, double *elapsed_ms) {
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ctx->tev[0], ctx->tev[1]));
     *elapsed_ms = (double)ms;
+    return RT_OK;
+}
+
+extern "C" int rt_set_option(rt_ctx *ctx, const char *name, double value) {
+    if (!ctx || !name) return RT_ERR_ARG;
+    std::string n(name);
+    if (n == "chunk_segments" && value >= 1.0)
+        ctx->opt_chunk_segments = value;
+    else if (n == "target_walkers" && value >= 1.0)
+        ctx->opt_target_walkers = value;
+    else
+        return fail(ctx, RT_ERR_ARG, "rt_set_option: unknown option or bad value: %s", name);
     return RT_OK;
 }

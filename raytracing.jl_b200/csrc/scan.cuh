@@ -88,4 +88,12 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(const Tin *in, Tout
     }
 }
 
+// grid-stride sum (total track length of a shard; only used to size chunks)
+__global__ void k_sum_double(const double *x, long long n, double *out) {
+    double s = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s += x[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
 }  // namespace rt

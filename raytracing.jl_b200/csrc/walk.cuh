@@ -1,5 +1,5 @@
 // walk.cuh -- the segmentation walk: _segmentize_track! (src/track.jl:106-178) as a count pass and a
-// fill pass over (track -> thread).  Two ways to take a step, producing identical results:
+// fill pass.  Two ways to take a step, producing identical results:
 //
 //   LITERAL  re-locate xp = q + tiny*(cos phi, sin phi) exactly like the reference (find_element through the
 //            nearest node, tolerant barycentric test, inboundary, intersections over all three edges);
@@ -8,8 +8,13 @@
 //            chord is (shared-edge hit, hit on the one other crossed edge); only that one line/line
 //            intersection is evaluated, with the reference's own formula so p, q, len are bit-identical.
 //
-// Threads of a warp alternate between a batch of FAST transitions and one LITERAL run-until-push, so the
-// rare literal steps of different tracks execute together instead of serialising the warp.
+// Parallel decomposition: a track is cut into CHUNKS at seed points x_j = p + (j/n)*len*(cos, sin).  A seed is
+// valid when x_j lies in a cell C whose chord is generic; the state "C has just been pushed" is then history
+// independent (intersections() only depends on the cell and the track), so walker j starts from it while walker
+// j-1 stops at its first push of C ("chunk hand-off").  Invalid seeds are void: the previous walker
+// simply continues.  One thread per (track, chunk); a warp holds the same chunk index of 32 consecutive tracks,
+// i.e. 32 adjacent parallel rays marching through the same cells.  Threads of a warp alternate between a batch
+// of FAST transitions and one LITERAL run-until-push, so the rare literal steps execute together.
 #pragma once
 #include "mesh_dev.cuh"
 
@@ -27,19 +32,36 @@ struct TrackSoA {
     long long *next_fwd, *next_bwd;
 };
 
+// chunk bookkeeping; per-chunk arrays are indexed cidx = unit*32 + lane, consecutive chunks of a track are 32 apart
+struct ChunkPlan {
+    int *nch;               // per track: number of chunks (>= 1)
+    int *unit_block;        // per warp-unit: which block of 32 consecutive tracks
+    long long *unit_base;   // per block: first unit; [n_blocks] = n_units
+    long long n_units;
+    int *seed_cell;         // >= 0: valid seed (cell already pushed by the previous walker); -1: void
+    int *seed_kexit;
+    double *seed_qx, *seed_qy;
+    int *count;             // segments pushed by this chunk (count pass; final after fix-up)
+    double *sum;            // sum of their lengths
+    int *endcode;           // END_* | status << 8
+    int *prefix;            // exclusive prefix of final counts inside the track
+};
+
+enum { END_HANDOFF = 0, END_TRACK = 1, END_ERROR = 2, END_CAP = 3 };
+
 struct WalkParams {
     DevMesh m;
-    long long n_tracks;   // tracks handled by this launch
-    long long trk_begin;  // first track (shard-local index) of this launch
+    long long n_tracks;     // tracks of the shard
+    long long trk_begin, trk_end;  // fill pass: only tracks in [trk_begin, trk_end) (batching); count pass: all
+    long long unit_begin, unit_end;
     TrackSoA t;
     AngleTabs ang;
+    ChunkPlan ch;
     double tiny, rtol, lmin;
     int k, max_iter;
     unsigned flags;
-    // count pass
-    int *count;
-    int *status;
-    // fill pass
+    int *count;   // per track (fix-up output)
+    int *status;  // per track
     const long long *offsets;  // shard-local exclusive scan of count
     long long offset_base;
     double *opx, *opy, *oqx, *oqy, *olen;
@@ -51,47 +73,181 @@ struct WalkParams {
 enum { MODE_FAST = 0, MODE_SLOW = 1, MODE_DONE = 2 };
 constexpr int kFastBatch = 16;
 constexpr long long kRunaway = 4000000;
+constexpr int kMaxChunksPerTrack = 4096;
 
+// ---- chunk planning -----------------------------------------------------------------------------------
+__global__ void k_plan_chunks(long long n_tracks, const double *len, double chunk_len, int *nch, int *blk_chunks) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    int n = 0;
+    if (t < n_tracks) {
+        double r = ceil(len[t] / chunk_len);
+        n = (r >= 1.0) ? (r > (double)kMaxChunksPerTrack ? kMaxChunksPerTrack : (int)r) : 1;
+        nch[t] = n;
+    }
+    int mx = __reduce_max_sync(0xffffffffu, n);
+    if ((threadIdx.x & 31) == 0 && t < n_tracks) blk_chunks[t >> 5] = mx;
+}
+
+__global__ void k_fill_units(long long n_blocks, const long long *unit_base, int *unit_block) {
+    long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    for (long long u = unit_base[b]; u < unit_base[b + 1]; ++u) unit_block[u] = (int)b;
+}
+
+struct TrackCtx {
+    Line trk;
+    double g, sx, sy, tlen, delta;
+    bool right;
+};
+
+__device__ __forceinline__ bool cell_clean(const CellRec &r, const Line &trk, double g, double clear) {
+    double thr = g * clear;
+    return (fabs(trk.a * r.vx[0] + trk.b * r.vy[0] + trk.c) >= thr) && (fabs(trk.a * r.vx[1] + trk.b * r.vy[1] + trk.c) >= thr) &&
+           (fabs(trk.a * r.vx[2] + trk.b * r.vy[2] + trk.c) >= thr);
+}
+
+// distance of a point from the nearest bounding-box line
+__device__ __forceinline__ double bbox_dist(const DevMesh &m, double x, double y) {
+    return fmin(fmin(fabs(x - m.bbmin[0]), fabs(x - m.bbmax[0])), fmin(fabs(y - m.bbmin[1]), fabs(y - m.bbmax[1])));
+}
+
+// ---- seeds: one thread per chunk j >= 1 ------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_seed(const __grid_constant__ WalkParams P) {
+    long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    long long unit = P.unit_begin + gw;
+    if (unit >= P.unit_end) return;
+    const DevMesh &m = P.m;
+    int b = P.ch.unit_block[unit];
+    int j = (int)(unit - P.ch.unit_base[b]);
+    long long t = 32LL * b + lane;
+    long long cidx = unit * 32 + lane;
+    if (t >= P.n_tracks) return;
+    int n = P.ch.nch[t];
+    if (j >= n) return;
+    P.ch.seed_cell[cidx] = -1;
+    if (j == 0) return;
+    int az = P.t.azim[t];
+    Line trk{P.t.a[t], P.t.b[t], P.t.c[t]};
+    double s = P.t.len[t] * ((double)j / (double)n);
+    double x = P.t.px[t] + s * P.ang.cosp[az], y = P.t.py[t] + s * P.ang.sinp[az];
+    bool right = P.ang.phi[az] < kPi / 2;
+    int c = find_element(m, x, y, 2, nullptr);
+    if (c < 0) return;
+    const CellRec &r = m.cells[c];
+    double clear = (double)r.clear;
+    if (!(clear >= 0.0) || !isfinite(clear)) return;  // boundary-band or degenerate cells never seed
+    double g = sqrt(trk.a * trk.a + trk.b * trk.b);
+    if (!cell_clean(r, trk, g, clear)) return;
+    // the seed point itself must be well inside (not merely tolerantly inside) the cell
+    {
+        double x1 = r.vx[0], y1 = r.vy[0], x2 = r.vx[1], y2 = r.vy[1], x3 = r.vx[2], y3 = r.vy[2];
+        double d = x1 * (y2 - y3) + y1 * (x3 - x2) + (x2 * y3 - y2 * x3);
+        double l1 = ((y2 - y3) * x + (x3 - x2) * y + (x2 * y3 - x3 * y2)) / d;
+        double l2 = ((y3 - y1) * x + (x1 - x3) * y + (x3 * y1 - x1 * y3)) / d;
+        double l3 = ((y1 - y2) * x + (x2 - x1) * y + (x1 * y2 - x2 * y1)) / d;
+        const double mrg = 1e-6;
+        if (!(l1 > mrg && l2 > mrg && l3 > mrg)) return;
+    }
+    P2 p, q;
+    int e_p, e_q;
+    if (intersections(m, c, trk, right, p, q, e_p, e_q) != 0) return;
+    if (e_q < 0 || e_p < 0) return;
+    double l = norm2(p.x - q.x, p.y - q.y);
+    if (!(l > P.lmin)) return;
+    P.ch.seed_cell[cidx] = c;
+    P.ch.seed_kexit[cidx] = e_q;
+    P.ch.seed_qx[cidx] = q.x;
+    P.ch.seed_qy[cidx] = q.y;
+}
+
+// ---- the walk ----------------------------------------------------------------------------------------------
 template <bool FILL>
 __global__ void __launch_bounds__(128) k_walk(const __grid_constant__ WalkParams P) {
     const unsigned FULL = 0xffffffffu;
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    int mode = MODE_DONE;
     const DevMesh &m = P.m;
+    long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    long long unit = P.unit_begin + gw;
+    if (unit >= P.unit_end) return;  // whole warp
+    int blk = P.ch.unit_block[unit];
+    int j = (int)(unit - P.ch.unit_base[blk]);
+    long long t = 32LL * blk + lane;
+    long long cidx = unit * 32 + lane;
 
-    // track state
+    int mode = MODE_DONE;
     Line trk{0, 0, 0};
     double tlen = 0, sx = 0, sy = 0, g = 0, delta = 0;
     bool right = true;
     double xpx = 0, xpy = 0;  // literal walk position
-    int prev = -1, nseg = 0, status = 0;
+    int prev = -1, nseg = 0, status = 0, endcode = END_TRACK;
     double sum = 0.0;
-    long long out = 0, t = 0;
-    // fast state: current cell, its exit edge, exit point, clearance bookkeeping
-    int cur = -1, kexit = -1;
+    long long out = 0;
+    int cur = -1, kexit = -1;  // fast state: current cell, its exit edge, exit point, clearance bookkeeping
     double qx = 0, qy = 0, clearA = INFINITY;
     bool clean = false;
+    int stop_cell = -1;  // count pass: hand-off cell of the next valid chunk
+    int limit = P.max_iter;
     long long slow_iters = 0;
     unsigned long long cnt[4] = {0, 0, 0, 0};
     const bool literal_only = (P.flags & 1u) != 0;
+    bool active = false;
 
-    if (i < P.n_tracks) {
-        t = P.trk_begin + i;
-        int az = P.t.azim[t];
-        trk.a = P.t.a[t];
-        trk.b = P.t.b[t];
-        trk.c = P.t.c[t];
-        tlen = P.t.len[t];
-        double phi = P.ang.phi[az];
-        right = phi < kPi / 2;  // isless(phi, pi/2), src/intersection.jl:153
-        sx = P.tiny * P.ang.cosp[az];  // advance_step: x + step*Point2D(cos phi, sin phi), src/point.jl:43
-        sy = P.tiny * P.ang.sinp[az];
-        delta = P.vol ? P.ang.delta_eff[az] : 0.0;
-        g = sqrt(trk.a * trk.a + trk.b * trk.b);
-        xpx = P.t.px[t] + sx;  // src/track.jl:114
-        xpy = P.t.py[t] + sy;
-        if (FILL) out = P.offsets[t] - P.offset_base;
-        mode = MODE_SLOW;
+    if (t < P.n_tracks && t >= P.trk_begin && t < P.trk_end) {
+        int n = P.ch.nch[t];
+        int seed = (j < n) ? (j == 0 ? -2 : P.ch.seed_cell[cidx]) : -1;
+        active = (seed != -1);
+        if (FILL && active) {
+            limit = P.ch.count[cidx];
+            active = limit > 0;
+        }
+        if (active) {
+            int az = P.t.azim[t];
+            trk.a = P.t.a[t];
+            trk.b = P.t.b[t];
+            trk.c = P.t.c[t];
+            tlen = P.t.len[t];
+            double phi = P.ang.phi[az];
+            right = phi < kPi / 2;         // isless(phi, pi/2), src/intersection.jl:153
+            sx = P.tiny * P.ang.cosp[az];  // advance_step: x + step*Point2D(cos phi, sin phi), src/point.jl:43
+            sy = P.tiny * P.ang.sinp[az];
+            delta = P.vol ? P.ang.delta_eff[az] : 0.0;
+            g = sqrt(trk.a * trk.a + trk.b * trk.b);
+            if (FILL) out = P.offsets[t] - P.offset_base + P.ch.prefix[cidx];
+            if (j == 0) {
+                xpx = P.t.px[t] + sx;  // src/track.jl:114
+                xpy = P.t.py[t] + sy;
+                mode = MODE_SLOW;
+            } else {
+                cur = seed;
+                kexit = P.ch.seed_kexit[cidx];
+                qx = P.ch.seed_qx[cidx];
+                qy = P.ch.seed_qy[cidx];
+                clearA = fabs((double)m.cells[cur].clear);
+                clean = true;  // k_seed verified it
+                prev = cur;
+                xpx = qx + sx;
+                xpy = qy + sy;
+                mode = literal_only ? MODE_SLOW : MODE_FAST;
+            }
+            if (!FILL) {
+                for (int jj = j + 1; jj < n; ++jj) {
+                    int sc = P.ch.seed_cell[cidx + 32LL * (jj - j)];
+                    if (sc >= 0) {
+                        stop_cell = sc;
+                        break;
+                    }
+                }
+                if (j > 0 && stop_cell == cur) {  // next seed sits in the same cell: this chunk is empty
+                    endcode = END_HANDOFF;
+                    mode = MODE_DONE;
+                }
+                if (limit <= 0) {  // while i < MAX_ITER never runs
+                    endcode = END_CAP;
+                    mode = MODE_DONE;
+                }
+            }
+        }
     }
 
     auto push = [&](int e, double ax, double ay, double bx, double by, double l) {
@@ -103,10 +259,17 @@ __global__ void __launch_bounds__(128) k_walk(const __grid_constant__ WalkParams
             P.oqy[o] = by;
             P.olen[o] = l;
             P.oelem[o] = e + 1;
-            if (P.vol) atomicAdd(&P.vol[e], delta * l);  // volumes[i] += delta_s[a]*l, src/trackgenerator.jl:382
         }
+        if (P.vol) atomicAdd(&P.vol[e], delta * l);  // volumes[i] += delta_s[a]*l, src/trackgenerator.jl:382
         sum += l;
         nseg += 1;
+        if (nseg >= limit) {  // while i < MAX_ITER (src/track.jl:119) / this chunk's final count in the fill pass
+            endcode = END_CAP;
+            mode = MODE_DONE;
+        } else if (!FILL && e == stop_cell) {
+            endcode = END_HANDOFF;
+            mode = MODE_DONE;
+        }
     };
 
     while (__any_sync(FULL, mode != MODE_DONE)) {
@@ -115,10 +278,6 @@ __global__ void __launch_bounds__(128) k_walk(const __grid_constant__ WalkParams
         for (int it = 0; it < kFastBatch; ++it) {
             if (!__any_sync(FULL, mode == MODE_FAST)) break;
             if (mode != MODE_FAST) continue;
-            if (nseg >= P.max_iter) {  // while i < MAX_ITER, src/track.jl:119
-                mode = MODE_DONE;
-                continue;
-            }
             bool ok = false;
             int B = m.cells[cur].nbr[kexit];
             if (B >= 0 && clean) {
@@ -126,7 +285,7 @@ __global__ void __launch_bounds__(128) k_walk(const __grid_constant__ WalkParams
                 double s0 = trk.a * rb.vx[0] + trk.b * rb.vy[0] + trk.c;
                 double s1 = trk.a * rb.vx[1] + trk.b * rb.vy[1] + trk.c;
                 double s2 = trk.a * rb.vx[2] + trk.b * rb.vy[2] + trk.c;
-                double clearB = (double)rb.clear;
+                double clearB = fabs((double)rb.clear);
                 double thr = g * fmax(clearA, clearB);
                 bool clear_ok = (fabs(s0) >= thr) && (fabs(s1) >= thr) && (fabs(s2) >= thr);
                 // edges k = (k, k+1): crossed iff the end points lie on opposite sides of the track line
@@ -146,8 +305,11 @@ __global__ void __launch_bounds__(128) k_walk(const __grid_constant__ WalkParams
                             // int_points are stored in edge order; order_intersection_points picks the first
                             bool in_first = kin < kout ? order_first(right, Xin, X) : !order_first(right, X, Xin);
                             double l = norm2(qx - X.x, qy - X.y);  // Segment(p, q): norm(p - q), src/segment.jl:32
-                            if (in_first && l > P.lmin) {
-                                push(B, qx, qy, X.x, X.y, l);
+                            bool accept = in_first && l > P.lmin;
+                            // cells touching the bounding-box band: the re-location points must not be `inboundary`
+                            if (accept && rb.clear < 0.0f) accept = bbox_dist(m, qx, qy) > 0.25 * l + 8.0 * P.tiny;
+                            if (accept) {
+                                double pxx = qx, pyy = qy;
                                 cur = B;
                                 kexit = kout;
                                 qx = X.x;
@@ -155,6 +317,7 @@ __global__ void __launch_bounds__(128) k_walk(const __grid_constant__ WalkParams
                                 clearA = clearB;
                                 ok = true;
                                 cnt[0]++;
+                                push(B, pxx, pyy, X.x, X.y, l);
                             }
                         }
                     }
@@ -171,23 +334,21 @@ __global__ void __launch_bounds__(128) k_walk(const __grid_constant__ WalkParams
         // ------------------------------------------------------------------ LITERAL phase (until one push)
         if (mode == MODE_SLOW) {
             while (true) {
-                if (nseg >= P.max_iter) {
-                    mode = MODE_DONE;
-                    break;
-                }
                 if (++slow_iters > kRunaway) {
                     status = 3;
+                    endcode = END_ERROR;
                     mode = MODE_DONE;
                     break;
                 }
                 cnt[1]++;
                 // find_element's result is discarded on boundary steps (src/track.jl:122-134): test the boundary first
                 if (inboundary(m, xpx, xpy, P.tiny)) {
-                    if (nseg == 0) {
+                    if (nseg == 0 && j == 0) {
                         xpx = xpx + sx;
                         xpy = xpy + sy;
                         continue;
                     }
+                    endcode = END_TRACK;
                     mode = MODE_DONE;
                     break;
                 }
@@ -196,6 +357,7 @@ __global__ void __launch_bounds__(128) k_walk(const __grid_constant__ WalkParams
                     e = find_element(m, xpx, xpy, P.k, &cnt[2]);
                     if (e < 0) {
                         status = 1;  // "Try increasing `k`", src/track.jl:141
+                        endcode = END_ERROR;
                         mode = MODE_DONE;
                         break;
                     }
@@ -210,6 +372,7 @@ __global__ void __launch_bounds__(128) k_walk(const __grid_constant__ WalkParams
                 int rc = intersections(m, e, trk, right, p, q, e_p, e_q);
                 if (rc) {
                     status = rc;
+                    endcode = END_ERROR;
                     mode = MODE_DONE;
                     break;
                 }
@@ -218,45 +381,82 @@ __global__ void __launch_bounds__(128) k_walk(const __grid_constant__ WalkParams
                     xpy = xpy + sy;
                     continue;
                 }
-                push(e, p.x, p.y, q.x, q.y, norm2(p.x - q.x, p.y - q.y));
                 xpx = q.x + sx;
                 xpy = q.y + sy;
                 prev = e;
-                if (literal_only || e_q < 0) break;  // stay literal
+                mode = MODE_SLOW;
+                push(e, p.x, p.y, q.x, q.y, norm2(p.x - q.x, p.y - q.y));
+                if (mode == MODE_DONE || literal_only || e_q < 0) break;
                 // arm the fast path: current cell, exit edge, and whether its vertices are clear of the track
                 const CellRec &rc_ = m.cells[e];
                 cur = e;
                 kexit = e_q;
                 qx = q.x;
                 qy = q.y;
-                clearA = (double)rc_.clear;
-                double thr = g * clearA;
-                clean = (fabs(trk.a * rc_.vx[0] + trk.b * rc_.vy[0] + trk.c) >= thr) &&
-                        (fabs(trk.a * rc_.vx[1] + trk.b * rc_.vy[1] + trk.c) >= thr) &&
-                        (fabs(trk.a * rc_.vx[2] + trk.b * rc_.vy[2] + trk.c) >= thr);
-                // even when this cell is not clean the neighbour test needs clean==true to pass, so only go FAST if so
+                clearA = fabs((double)rc_.clear);
+                clean = cell_clean(rc_, trk, g, clearA);
                 mode = clean ? MODE_FAST : MODE_SLOW;
                 break;
             }
         }
     }
 
-    if (i < P.n_tracks) {
-        if (!FILL) {
-            // sum(l.(segments)) ~ track.l, src/track.jl:171-175 (errors thrown earlier skip this check)
-            if (status == 0 && !isapprox(tlen, sum, 0.0, P.rtol)) status = 2;
-            P.count[t] = nseg;
-            P.status[t] = status;
-        }
+    if (!FILL && t < P.n_tracks && j < P.ch.nch[t]) {
+        P.ch.count[cidx] = active ? nseg : 0;
+        P.ch.sum[cidx] = sum;
+        P.ch.endcode[cidx] = active ? (endcode | (status << 8)) : (END_HANDOFF | (0 << 8));
     }
     if (P.counters) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             unsigned long long v = cnt[q];
             for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
-            if ((threadIdx.x & 31) == 0 && v) atomicAdd(&P.counters[q], v);
+            if (lane == 0 && v) atomicAdd(&P.counters[q], v);
         }
     }
+    (void)tlen;
+}
+
+// ---- per-track fix-up: combine the chunks of a track exactly like one serial walk would have ended ----------
+//  * a chunk that ended with an error / at the track end / at the MAX_ITER cap ends the track: later chunks are dropped
+//  * the total is capped at max_iter (src/track.jl:119); the length check (src/track.jl:171-175) uses the chunk sums
+__global__ void k_fixup_tracks(const __grid_constant__ WalkParams P) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= P.n_tracks) return;
+    int n = P.ch.nch[t];
+    long long blk = t >> 5;
+    int lane = (int)(t & 31);
+    long long c0 = P.ch.unit_base[blk] * 32 + lane;
+    int total = 0, status = 0;
+    double sum = 0.0;
+    bool open = true, truncated = false;
+    for (int j = 0; j < n; ++j) {
+        long long cidx = c0 + 32LL * j;
+        bool valid = (j == 0) || P.ch.seed_cell[cidx] >= 0;
+        int cnt = (valid && open) ? P.ch.count[cidx] : 0;
+        if (valid && open) {
+            int ec = P.ch.endcode[cidx];
+            int end = ec & 255, st = ec >> 8;
+            if (total + cnt >= P.max_iter) {
+                if (total + cnt > P.max_iter) truncated = true;
+                cnt = P.max_iter - total;
+                open = false;
+            }
+            sum += P.ch.sum[cidx];
+            if (end == END_ERROR) {
+                status = st;
+                open = false;
+            } else if (end != END_HANDOFF) {
+                open = false;  // END_TRACK, or END_CAP inside one chunk
+            }
+        }
+        P.ch.prefix[cidx] = total;
+        P.ch.count[cidx] = cnt;
+        total += cnt;
+    }
+    if (status == 0 && (truncated || !isapprox(P.t.len[t], sum, 0.0, P.rtol))) status = 2;
+    P.count[t] = total;
+    P.status[t] = status;
 }
 
 }  // namespace rt

@@ -27,13 +27,16 @@ def bcs_of(codes):
     return rt.BoundaryConditions(top=t, bottom=b, right=r, left=l)
 
 
-def run_both(model, n_azim, delta, bcs=(0, 0, 0, 0), flags=0, k=5, capacity=0):
+def run_both(model, n_azim, delta, bcs=(0, 0, 0, 0), flags=0, k=5, capacity=0, chunk_segments=None):
     mesh = rt.Mesh(model)
     otg = OracleTrackGenerator(OracleMesh.from_mesh(mesh), n_azim, delta, bcs=bcs)
     otg.trace()
     otg.segmentize(k=k, check=False, nthreads=8)
     tg = rt.TrackGenerator(mesh, n_azim, delta, bcs=bcs_of(bcs))
     rt.trace_(tg)
+    if chunk_segments:
+        tg.set_option("chunk_segments", chunk_segments)
+        tg.set_option("target_walkers", 1e9)
     if capacity:
         from raytracing_jl_b200 import _lib
         _lib.lib().rt_set_segment_capacity(tg._ctx, capacity)
@@ -108,10 +111,11 @@ def test_trace_matches_oracle_bitwise(pincell_model, n_azim, delta, bcs):
 
 
 # ---- segmentize! -------------------------------------------------------------------------------------
-@pytest.mark.parametrize("flags", [0, rt.RT_SEG_LITERAL])
+@pytest.mark.parametrize("flags,chunk", [(0, None), (rt.RT_SEG_LITERAL, None), (rt.RT_SEG_NO_CHUNKS, None),
+                                         (rt.RT_SEG_LITERAL | rt.RT_SEG_NO_CHUNKS, None), (0, 4), (0, 1), (rt.RT_SEG_LITERAL, 3)])
 @pytest.mark.parametrize("n_azim,delta", [(8, 0.02), (16, 0.08), (32, 0.01), (4, 0.8)])
-def test_pincell_segments_match_oracle(pincell_model, n_azim, delta, flags):
-    otg, tg = run_both(pincell_model, n_azim, delta, flags=flags)
+def test_pincell_segments_match_oracle(pincell_model, n_azim, delta, flags, chunk):
+    otg, tg = run_both(pincell_model, n_azim, delta, flags=flags, chunk_segments=chunk)
     assert_tracks_equal(otg, tg)
     assert_segments_equal(otg, tg)
     assert_volumes_close(otg, tg)
@@ -140,6 +144,9 @@ def test_jittered_mesh_matches_oracle(seed, n, n_azim, delta):
     assert_volumes_close(otg, tg)
     st = tg.stats()
     assert st["fast_transitions"] > 0.8 * tg.n_segments
+    otg, tg = run_both(model, n_azim, delta, chunk_segments=5)  # many tiny chunks: exercises every hand-off rule
+    assert_segments_equal(otg, tg)
+    assert_volumes_close(otg, tg)
 
 
 def test_offset_domain_and_rectangle():
@@ -179,8 +186,9 @@ def test_structured_mesh_exact_vertex_crossings():
     assert_segments_equal(otg, tg)
 
 
-def test_batched_fill_equals_single_shot(pincell_model):
-    otg, tg = run_both(pincell_model, 32, 0.01, capacity=20000)
+@pytest.mark.parametrize("chunk", [None, 7])
+def test_batched_fill_equals_single_shot(pincell_model, chunk):
+    otg, tg = run_both(pincell_model, 32, 0.01, capacity=20000, chunk_segments=chunk)
     assert tg.n_segments == otg.n_segments and np.array_equal(tg.segment_offsets, otg.seg_offsets)
     # only the last batch is resident: compare it with the tail of the oracle's arrays
     s = tg.segments
@@ -204,6 +212,13 @@ def test_idempotent_and_max_iter(pincell_model):
     # MAX_ITER cap (src/track.jl:104,119): tracks stop at max_iter segments and fail the length check
     rt.segmentize_(tg, max_iter=10, check=False)
     assert np.diff(tg.segment_offsets).max() == 10 and tg.bad_status == 2
+    tg.set_option("chunk_segments", 3)
+    tg.set_option("target_walkers", 1e9)
+    rt.segmentize_(tg, max_iter=10, check=False)
+    assert np.diff(tg.segment_offsets).max() == 10 and tg.bad_status == 2
+    off = tg.segment_offsets
+    u = 0
+    assert np.array_equal(tg.segments["element"][off[u]:off[u + 1]], a["element"][:10])
 
 
 def test_error_paths(pincell_model):
