@@ -20,7 +20,23 @@ struct __align__(32) EdgeRec {
     double a, b, c, len;
 };
 
+// 96-byte record of the directed half-edge h = 3*cell + k, read when a track ENTERS `cell` through its edge
+// k = (v_k, v_k+1): everything one fast transition needs in a single round trip (three 32 B sectors).
+struct __align__(32) HalfEdge {
+    double ax, ay;      // apex v_k+2
+    int tw1, tw2;       // entry half-edge of the neighbour across edge k+1 = (v_k+1, apex) / k+2 = (apex, v_k),
+                        // encoded (3*cell' + k') << 1 | flip (flip: end points in opposite order); -1 on the boundary
+    float clear;        // = CellRec::clear of this cell
+    int pad0;
+    double a1, b1, c1;  // general_form(v_k+1, apex)   (src/intersection.jl:57, the cell's stored orientation)
+    double a2, b2, c2;  // general_form(apex, v_k)
+    double pad1[2];
+};
+static_assert(sizeof(HalfEdge) == 96, "HalfEdge must be 96 bytes");
+
 struct DevMesh {
+    const HalfEdge *he;  // [3*cell + k]
+    const int *twin;     // [3*cell + k]: encoded entry half-edge of the neighbour across edge k (as tw1/tw2)
     int n_nodes, n_cells;
     const double2 *xy;      // node coordinates
     const int *cell_nodes;  // 3*n_cells, 0-based, stored (Gridap) order
@@ -144,17 +160,34 @@ __global__ void k_cell_records(DevMesh m, const int *nbr, CellRec *cells, EdgeRe
 //   reach R = (8*rtol + 64*eps*(S/hmin_c)^2) * Lmax      (how far outside a cell its tolerant test can pass)
 //   clear_c = 8 * R / sigma_c ; stored NEGATIVE for cells with a vertex inside the bounding-box band (the fast path
 //   then also checks that the re-location points are not `inboundary`), +inf for degenerate cells (always literal)
-__global__ void k_finalize_clear(DevMesh m, CellRec *cells, const float *qual, const float *bdist, const MeshScalars *sc,
-                                 double tiny) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= m.n_cells) return;
-    const CellRec &r = cells[c];
+__device__ __forceinline__ double cell_hmin(const DevMesh &m, const CellRec &r, int c) {
     double lmax = 0.0;
     for (int k = 0; k < 3; ++k) lmax = fmax(lmax, m.edges[3 * c + k].len);
     double area2 = fabs((r.vx[1] - r.vx[0]) * (r.vy[2] - r.vy[0]) - (r.vx[2] - r.vx[0]) * (r.vy[1] - r.vy[0]));
-    double hmin = area2 / lmax;
+    return area2 / lmax;
+}
+
+// reach of every cell, max-reduced onto its nodes (so a cell can take the max over its whole vertex star)
+__global__ void k_node_reach(DevMesh m, const CellRec *cells, const MeshScalars *sc, float *node_reach) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m.n_cells) return;
+    double hmin = cell_hmin(m, cells[c], c);
     double ratio = sc->smax / hmin;
     double reach = (8.0 * kRtol + 64.0 * 2.220446049250313e-16 * ratio * ratio) * sc->lmax;
+    float rf = (float)reach;
+    if (!(rf >= reach)) rf = nextafterf(rf, INFINITY);
+    if (!(hmin > 0.0) || !isfinite(reach)) rf = INFINITY;
+    for (int k = 0; k < 3; ++k) atomicMax((unsigned *)&node_reach[m.cell_nodes[3 * c + k]], __float_as_uint(rf));
+}
+
+__global__ void k_finalize_clear(DevMesh m, CellRec *cells, HalfEdge *he, const float *qual, const float *bdist,
+                                 const MeshScalars *sc, const float *node_reach, double tiny) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m.n_cells) return;
+    const CellRec &r = cells[c];
+    double hmin = cell_hmin(m, r, c);
+    double reach = 0.0;
+    for (int k = 0; k < 3; ++k) reach = fmax(reach, (double)node_reach[m.cell_nodes[3 * c + k]]);
     double clear = 8.0 * reach * (double)qual[c] * 1.001;
     bool boundary = !((double)bdist[c] > 16.0 * tiny + 1e-12 * sc->smax);
     float cf = (float)clear;
@@ -164,6 +197,51 @@ __global__ void k_finalize_clear(DevMesh m, CellRec *cells, const float *qual, c
     else if (boundary)
         cf = -cf;
     cells[c].clear = cf;
+    for (int k = 0; k < 3; ++k) he[3 * c + k].clear = cf;
+}
+
+// twin[3c+k]: where a track that leaves cell c through edge k = (v_k, v_k+1) enters the neighbour
+__global__ void k_twins(int n_cells, const int *cell_nodes, const int *nbr, int *twin) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= 3 * (int64_t)n_cells) return;
+    int c = (int)(t / 3), k = (int)(t % 3);
+    int n1 = nbr[t];
+    int enc = -1;
+    if (n1 >= 0) {
+        int a = cell_nodes[3 * c + k], b = cell_nodes[3 * c + (k + 1) % 3];
+        const int *nn = &cell_nodes[3 * n1];
+        for (int kk = 0; kk < 3; ++kk) {
+            int a2 = nn[kk], b2 = nn[(kk + 1) % 3];
+            if (a2 == b && b2 == a) enc = ((3 * n1 + kk) << 1) | 1;  // opposite order (consistently oriented pair)
+            if (a2 == a && b2 == b) enc = ((3 * n1 + kk) << 1) | 0;
+        }
+    }
+    twin[t] = enc;
+}
+
+__global__ void k_half_edges(DevMesh m, const CellRec *cells, const int *twin, HalfEdge *he) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= 3 * (int64_t)m.n_cells) return;
+    int c = (int)(t / 3), k = (int)(t % 3);
+    int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
+    const CellRec &r = cells[c];
+    const EdgeRec e1 = m.edges[3 * c + k1], e2 = m.edges[3 * c + k2];
+    HalfEdge h;
+    h.ax = r.vx[k2];
+    h.ay = r.vy[k2];
+    h.tw1 = twin[3 * c + k1];
+    h.tw2 = twin[3 * c + k2];
+    h.clear = INFINITY;
+    h.pad0 = 0;
+    h.a1 = e1.a;
+    h.b1 = e1.b;
+    h.c1 = e1.c;
+    h.a2 = e2.a;
+    h.b2 = e2.b;
+    h.c2 = e2.c;
+    h.pad1[0] = e1.len;
+    h.pad1[1] = e2.len;
+    he[t] = h;
 }
 
 // ---- uniform node grid -------------------------------------------------------------------------

@@ -50,7 +50,7 @@ struct rt_ctx {
     bool has_mesh = false;
     DevMesh m{};
     DevBuf b_xy, b_cell_nodes, b_nc_ptrs, b_nc_data, b_nbr, b_cells, b_edges, b_qual, b_bdist, b_sc, b_grid_ptrs,
-        b_grid_nodes;
+        b_grid_nodes, b_twin, b_he, b_node_reach;
     double clear_tiny = -1.0;
     double smax = 0.0, lmax = 0.0;
 
@@ -172,6 +172,7 @@ extern "C" void rt_destroy(rt_ctx *ctx) {
                      &ctx->b_ang_d,   &ctx->b_ang_i,      &ctx->b_trk_d,    &ctx->b_trk_i,   &ctx->b_trk_l,   &ctx->b_trk_c,
                      &ctx->b_err,     &ctx->b_count,      &ctx->b_status,   &ctx->b_offsets, &ctx->b_tile,    &ctx->b_vol,
                      &ctx->b_voln,    &ctx->b_counters,   &ctx->b_bad,      &ctx->b_seg_d,   &ctx->b_seg_e,
+                     &ctx->b_twin,    &ctx->b_he,         &ctx->b_node_reach,
                      &ctx->b_nch,     &ctx->b_blk_chunks, &ctx->b_unit_base, &ctx->b_unit_block, &ctx->b_ch_i, &ctx->b_ch_d};
     for (DevBuf *b : all) release(*b);
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
@@ -275,6 +276,16 @@ extern "C" int rt_mesh_upload(rt_ctx *ctx, int32_t n_nodes, const double *xy, in
     k_cell_records<<<blocks_for(n_cells, 128), 128, 0, st>>>(m, (const int *)ctx->b_nbr.p, (CellRec *)ctx->b_cells.p,
                                                              (EdgeRec *)ctx->b_edges.p, (float *)ctx->b_qual.p,
                                                              (float *)ctx->b_bdist.p, (MeshScalars *)ctx->b_sc.p);
+    CK(ensure(ctx->b_twin, sizeof(int) * 3 * (size_t)n_cells));
+    CK(ensure(ctx->b_he, sizeof(HalfEdge) * 3 * (size_t)n_cells));
+    CK(ensure(ctx->b_node_reach, sizeof(float) * (size_t)n_nodes));
+    m.twin = (const int *)ctx->b_twin.p;
+    m.he = (const HalfEdge *)ctx->b_he.p;
+    k_twins<<<blocks_for(3LL * n_cells, 256), 256, 0, st>>>(n_cells, m.cell_nodes, (const int *)ctx->b_nbr.p, (int *)ctx->b_twin.p);
+    k_half_edges<<<blocks_for(3LL * n_cells, 128), 128, 0, st>>>(m, (const CellRec *)ctx->b_cells.p, m.twin, (HalfEdge *)ctx->b_he.p);
+    CK(cudaMemsetAsync(ctx->b_node_reach.p, 0, sizeof(float) * (size_t)n_nodes, st));
+    k_node_reach<<<blocks_for(n_cells, 128), 128, 0, st>>>(m, (const CellRec *)ctx->b_cells.p, (const MeshScalars *)ctx->b_sc.p,
+                                                           (float *)ctx->b_node_reach.p);
     // grid: count -> scan -> fill
     DevBuf counts, cursor;
     CK(ensure(counts, sizeof(int) * n_bins));
@@ -584,7 +595,7 @@ static int ensure_segment_buffers(rt_ctx *ctx, long long want) {
     release(ctx->b_seg_d);
     release(ctx->b_seg_e);
     ctx->cap = 0;
-    size_t n = (size_t)std::max<long long>(want, 1);
+    size_t n = ((size_t)std::max<long long>(want, 1) + 15) & ~(size_t)15;  // every SoA column stays 32-byte aligned
     CK(ensure(ctx->b_seg_d, sizeof(double) * 5 * n));
     CK(ensure(ctx->b_seg_e, sizeof(int) * n));
     double *d = (double *)ctx->b_seg_d.p;
@@ -616,9 +627,10 @@ extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rt
     ctx->vol_valid = false;
 
     if (ctx->clear_tiny != tiny_step) {
-        k_finalize_clear<<<blocks_for(m.n_cells, 128), 128, 0, st>>>(m, (CellRec *)ctx->b_cells.p, (const float *)ctx->b_qual.p,
-                                                                     (const float *)ctx->b_bdist.p, (const MeshScalars *)ctx->b_sc.p,
-                                                                     tiny_step);
+        k_finalize_clear<<<blocks_for(m.n_cells, 128), 128, 0, st>>>(m, (CellRec *)ctx->b_cells.p, (HalfEdge *)ctx->b_he.p,
+                                                                     (const float *)ctx->b_qual.p, (const float *)ctx->b_bdist.p,
+                                                                     (const MeshScalars *)ctx->b_sc.p,
+                                                                     (const float *)ctx->b_node_reach.p, tiny_step);
         CK(cudaGetLastError());
         ctx->clear_tiny = tiny_step;
     }

@@ -161,11 +161,28 @@ __global__ void __launch_bounds__(128) k_seed(const __grid_constant__ WalkParams
     P.ch.seed_qy[cidx] = q.y;
 }
 
+// ---- 256-bit / 128-bit read-only loads and 256-bit stores (LDG.E.ENL2.256 / STG.E.ENL2.256 on sm_100a) ---------------
+__device__ __forceinline__ void ldg256(const void *p, double &a, double &b, double &c, double &d) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void ldg128(const void *p, double &a, double &b) {
+    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
+}
+__device__ __forceinline__ void stg256(void *p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+constexpr int kWalkThreads = 128;
+
 // ---- the walk ----------------------------------------------------------------------------------------------
 template <bool FILL>
-__global__ void __launch_bounds__(128) k_walk(const __grid_constant__ WalkParams P) {
+__global__ void __launch_bounds__(kWalkThreads) k_walk(const __grid_constant__ WalkParams P) {
     const unsigned FULL = 0xffffffffu;
     const DevMesh &m = P.m;
+    // fill pass: every thread stages 4 consecutive segments and writes them as full, aligned 32-byte sectors
+    __shared__ double s_buf[FILL ? 5 * 4 * kWalkThreads : 1];
+    __shared__ int s_el[FILL ? 4 * kWalkThreads : 1];
+    const int tid = threadIdx.x;
     long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     long long unit = P.unit_begin + gw;
@@ -177,14 +194,16 @@ __global__ void __launch_bounds__(128) k_walk(const __grid_constant__ WalkParams
 
     int mode = MODE_DONE;
     Line trk{0, 0, 0};
-    double tlen = 0, sx = 0, sy = 0, g = 0, delta = 0;
+    double sx = 0, sy = 0, g = 0, delta = 0;
     bool right = true;
     double xpx = 0, xpy = 0;  // literal walk position
     int prev = -1, nseg = 0, status = 0, endcode = END_TRACK;
     double sum = 0.0;
     long long out = 0;
-    int cur = -1, kexit = -1;  // fast state: current cell, its exit edge, exit point, clearance bookkeeping
-    double qx = 0, qy = 0, clearA = INFINITY;
+    // fast state: last pushed cell, the half-edge through which the next cell is entered (-1: boundary), the
+    // signed distances of that edge's end points from the track line (in the half-edge's order), the exit point
+    int cur = -1, hB = -1;
+    double sp = 0, sq = 0, qx = 0, qy = 0, clearA = INFINITY;
     bool clean = false;
     int stop_cell = -1;  // count pass: hand-off cell of the next valid chunk
     int limit = P.max_iter;
@@ -192,6 +211,27 @@ __global__ void __launch_bounds__(128) k_walk(const __grid_constant__ WalkParams
     unsigned long long cnt[4] = {0, 0, 0, 0};
     const bool literal_only = (P.flags & 1u) != 0;
     bool active = false;
+
+    // arm the fast path after cell e was pushed with exit edge e_q (local index) and exit point (ex, ey)
+    auto arm = [&](int e, int e_q, double ex, double ey) {
+        const CellRec &r = m.cells[e];
+        cur = e;
+        qx = ex;
+        qy = ey;
+        clearA = fabs((double)r.clear);
+        double s[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) s[q] = trk.a * r.vx[q] + trk.b * r.vy[q] + trk.c;
+        double thr = g * clearA;
+        double sa = e_q == 0 ? s[0] : (e_q == 1 ? s[1] : s[2]);
+        double sb = e_q == 0 ? s[1] : (e_q == 1 ? s[2] : s[0]);
+        clean = (fabs(s[0]) >= thr) && (fabs(s[1]) >= thr) && (fabs(s[2]) >= thr) && ((sa > 0) != (sb > 0));
+        int enc = m.twin[3 * e + e_q];
+        hB = enc < 0 ? -1 : (enc >> 1);
+        bool flip = (enc & 1) != 0;
+        sp = flip ? sb : sa;
+        sq = flip ? sa : sb;
+    };
 
     if (t < P.n_tracks && t >= P.trk_begin && t < P.trk_end) {
         int n = P.ch.nch[t];
@@ -206,7 +246,6 @@ __global__ void __launch_bounds__(128) k_walk(const __grid_constant__ WalkParams
             trk.a = P.t.a[t];
             trk.b = P.t.b[t];
             trk.c = P.t.c[t];
-            tlen = P.t.len[t];
             double phi = P.ang.phi[az];
             right = phi < kPi / 2;         // isless(phi, pi/2), src/intersection.jl:153
             sx = P.tiny * P.ang.cosp[az];  // advance_step: x + step*Point2D(cos phi, sin phi), src/point.jl:43
@@ -219,16 +258,11 @@ __global__ void __launch_bounds__(128) k_walk(const __grid_constant__ WalkParams
                 xpy = P.t.py[t] + sy;
                 mode = MODE_SLOW;
             } else {
-                cur = seed;
-                kexit = P.ch.seed_kexit[cidx];
-                qx = P.ch.seed_qx[cidx];
-                qy = P.ch.seed_qy[cidx];
-                clearA = fabs((double)m.cells[cur].clear);
-                clean = true;  // k_seed verified it
+                arm(seed, P.ch.seed_kexit[cidx], P.ch.seed_qx[cidx], P.ch.seed_qy[cidx]);  // k_seed verified `clean`
                 prev = cur;
                 xpx = qx + sx;
                 xpy = qy + sy;
-                mode = literal_only ? MODE_SLOW : MODE_FAST;
+                mode = (literal_only || !clean) ? MODE_SLOW : MODE_FAST;
             }
             if (!FILL) {
                 for (int jj = j + 1; jj < n; ++jj) {
@@ -253,12 +287,36 @@ __global__ void __launch_bounds__(128) k_walk(const __grid_constant__ WalkParams
     auto push = [&](int e, double ax, double ay, double bx, double by, double l) {
         if (FILL) {
             long long o = out + nseg;
-            P.opx[o] = ax;
-            P.opy[o] = ay;
-            P.oqx[o] = bx;
-            P.oqy[o] = by;
-            P.olen[o] = l;
-            P.oelem[o] = e + 1;
+            int k = (int)(o & 3);
+            s_buf[(0 * 4 + k) * kWalkThreads + tid] = ax;
+            s_buf[(1 * 4 + k) * kWalkThreads + tid] = ay;
+            s_buf[(2 * 4 + k) * kWalkThreads + tid] = bx;
+            s_buf[(3 * 4 + k) * kWalkThreads + tid] = by;
+            s_buf[(4 * 4 + k) * kWalkThreads + tid] = l;
+            s_el[k * kWalkThreads + tid] = e + 1;
+            bool last = nseg + 1 >= limit;
+            if (k == 3 || last) {
+                long long g0 = o & ~3LL;
+                int kf = (int)((g0 > out ? g0 : out) - g0);
+                if (kf == 0 && k == 3) {
+                    double *dst[5] = {P.opx, P.opy, P.oqx, P.oqy, P.olen};
+#pragma unroll
+                    for (int a = 0; a < 5; ++a)
+                        stg256(dst[a] + g0, s_buf[(a * 4 + 0) * kWalkThreads + tid], s_buf[(a * 4 + 1) * kWalkThreads + tid],
+                               s_buf[(a * 4 + 2) * kWalkThreads + tid], s_buf[(a * 4 + 3) * kWalkThreads + tid]);
+                    *reinterpret_cast<int4 *>(P.oelem + g0) = make_int4(s_el[0 * kWalkThreads + tid], s_el[1 * kWalkThreads + tid],
+                                                                        s_el[2 * kWalkThreads + tid], s_el[3 * kWalkThreads + tid]);
+                } else {
+                    for (int kk = kf; kk <= k; ++kk) {
+                        P.opx[g0 + kk] = s_buf[(0 * 4 + kk) * kWalkThreads + tid];
+                        P.opy[g0 + kk] = s_buf[(1 * 4 + kk) * kWalkThreads + tid];
+                        P.oqx[g0 + kk] = s_buf[(2 * 4 + kk) * kWalkThreads + tid];
+                        P.oqy[g0 + kk] = s_buf[(3 * 4 + kk) * kWalkThreads + tid];
+                        P.olen[g0 + kk] = s_buf[(4 * 4 + kk) * kWalkThreads + tid];
+                        P.oelem[g0 + kk] = s_el[kk * kWalkThreads + tid];
+                    }
+                }
+            }
         }
         if (P.vol) atomicAdd(&P.vol[e], delta * l);  // volumes[i] += delta_s[a]*l, src/trackgenerator.jl:382
         sum += l;
@@ -279,46 +337,54 @@ __global__ void __launch_bounds__(128) k_walk(const __grid_constant__ WalkParams
             if (!__any_sync(FULL, mode == MODE_FAST)) break;
             if (mode != MODE_FAST) continue;
             bool ok = false;
-            int B = m.cells[cur].nbr[kexit];
-            if (B >= 0 && clean) {
-                const CellRec rb = m.cells[B];
-                double s0 = trk.a * rb.vx[0] + trk.b * rb.vy[0] + trk.c;
-                double s1 = trk.a * rb.vx[1] + trk.b * rb.vy[1] + trk.c;
-                double s2 = trk.a * rb.vx[2] + trk.b * rb.vy[2] + trk.c;
-                double clearB = fabs((double)rb.clear);
+            if (hB >= 0 && clean) {
+                const HalfEdge *hp = m.he + hB;
+                double ax, ay, w0, w1, a1, b1, c1, a2, b2, c2;
+                ldg256(hp, ax, ay, w0, w1);
+                ldg256(reinterpret_cast<const char *>(hp) + 32, a1, b1, c1, a2);
+                ldg128(reinterpret_cast<const char *>(hp) + 64, b2, c2);
+                int tw1 = __double2loint(w0), tw2 = __double2hiint(w0);
+                float clearf = __int_as_float(__double2loint(w1));
+                double sa = trk.a * ax + trk.b * ay + trk.c;
+                double clearB = fabs((double)clearf);
                 double thr = g * fmax(clearA, clearB);
-                bool clear_ok = (fabs(s0) >= thr) && (fabs(s1) >= thr) && (fabs(s2) >= thr);
-                // edges k = (k, k+1): crossed iff the end points lie on opposite sides of the track line
-                bool c0 = (s0 > 0) != (s1 > 0), c1 = (s1 > 0) != (s2 > 0), c2 = (s2 > 0) != (s0 > 0);
-                int kin = (rb.nbr[0] == cur) ? 0 : ((rb.nbr[1] == cur) ? 1 : ((rb.nbr[2] == cur) ? 2 : -1));
-                int ncross = (int)c0 + (int)c1 + (int)c2;
-                if (clear_ok && ncross == 2 && kin >= 0) {
-                    bool cin = kin == 0 ? c0 : (kin == 1 ? c1 : c2);
-                    int kout = (c0 && kin != 0) ? 0 : ((c1 && kin != 1) ? 1 : 2);
-                    if (cin) {
-                        const EdgeRec e = m.edges[3 * B + kout];
-                        Line L{e.a, e.b, e.c};
-                        P2 X;
-                        bool par = intersection(trk, L, X);  // same formula as src/intersection.jl:127-138
-                        if (!par) {
-                            P2 Xin{qx, qy};
-                            // int_points are stored in edge order; order_intersection_points picks the first
-                            bool in_first = kin < kout ? order_first(right, Xin, X) : !order_first(right, X, Xin);
-                            double l = norm2(qx - X.x, qy - X.y);  // Segment(p, q): norm(p - q), src/segment.jl:32
-                            bool accept = in_first && l > P.lmin;
-                            // cells touching the bounding-box band: the re-location points must not be `inboundary`
-                            if (accept && rb.clear < 0.0f) accept = bbox_dist(m, qx, qy) > 0.25 * l + 8.0 * P.tiny;
-                            if (accept) {
-                                double pxx = qx, pyy = qy;
-                                cur = B;
-                                kexit = kout;
-                                qx = X.x;
-                                qy = X.y;
-                                clearA = clearB;
-                                ok = true;
-                                cnt[0]++;
-                                push(B, pxx, pyy, X.x, X.y, l);
-                            }
+                bool clear_ok = (fabs(sa) >= thr) && (fabs(sp) >= thr) && (fabs(sq) >= thr);
+                // the entry edge (v_k, v_k+1) is crossed (sp, sq of opposite sign); the exit is the other edge whose
+                // non-apex end lies on the opposite side of the apex: edge k+1 = (v_k+1, apex) or k+2 = (apex, v_k)
+                bool exit1 = (sa > 0) != (sq > 0);
+                int cellB = hB / 3;
+                int kin = hB - 3 * cellB;
+                if (clear_ok) {
+                    Line L;
+                    L.a = exit1 ? a1 : a2;
+                    L.b = exit1 ? b1 : b2;
+                    L.c = exit1 ? c1 : c2;
+                    P2 X;
+                    bool par = intersection(trk, L, X);  // same formula as src/intersection.jl:127-138
+                    if (!par) {
+                        P2 Xin{qx, qy};
+                        // int_points are stored in edge-index order; order_intersection_points picks the first
+                        bool kin_lt_kout = (kin == 0) || (kin == 1 && exit1);
+                        bool in_first = kin_lt_kout ? order_first(right, Xin, X) : !order_first(right, X, Xin);
+                        double l = norm2(qx - X.x, qy - X.y);  // Segment(p, q): norm(p - q), src/segment.jl:32
+                        bool accept = in_first && l > P.lmin;
+                        // cells touching the bounding-box band: the re-location points must not be `inboundary`
+                        if (accept && clearf < 0.0f) accept = bbox_dist(m, qx, qy) > 0.25 * l + 8.0 * P.tiny;
+                        if (accept) {
+                            double pxx = qx, pyy = qy;
+                            int enc = exit1 ? tw1 : tw2;
+                            double na = exit1 ? sq : sa, nb = exit1 ? sa : sp;  // s at the exit edge's ordered end points
+                            bool flip = (enc & 1) != 0;
+                            sp = flip ? nb : na;
+                            sq = flip ? na : nb;
+                            hB = enc < 0 ? -1 : (enc >> 1);
+                            cur = cellB;
+                            qx = X.x;
+                            qy = X.y;
+                            clearA = clearB;
+                            ok = true;
+                            cnt[0]++;
+                            push(cellB, pxx, pyy, X.x, X.y, l);
                         }
                     }
                 }
@@ -387,14 +453,7 @@ __global__ void __launch_bounds__(128) k_walk(const __grid_constant__ WalkParams
                 mode = MODE_SLOW;
                 push(e, p.x, p.y, q.x, q.y, norm2(p.x - q.x, p.y - q.y));
                 if (mode == MODE_DONE || literal_only || e_q < 0) break;
-                // arm the fast path: current cell, exit edge, and whether its vertices are clear of the track
-                const CellRec &rc_ = m.cells[e];
-                cur = e;
-                kexit = e_q;
-                qx = q.x;
-                qy = q.y;
-                clearA = fabs((double)rc_.clear);
-                clean = cell_clean(rc_, trk, g, clearA);
+                arm(e, e_q, q.x, q.y);
                 mode = clean ? MODE_FAST : MODE_SLOW;
                 break;
             }
@@ -414,7 +473,6 @@ __global__ void __launch_bounds__(128) k_walk(const __grid_constant__ WalkParams
             if (lane == 0 && v) atomicAdd(&P.counters[q], v);
         }
     }
-    (void)tlen;
 }
 
 // ---- per-track fix-up: combine the chunks of a track exactly like one serial walk would have ended ----------
