@@ -1,0 +1,140 @@
+# RayTracingB200.jl -- the `ccall` glue a RayTracing.jl maintainer adds to route `trace!` / `segmentize!`
+# through librt_b200.so (C ABI: include/rt_b200.h).  `include` it at the end of src/RayTracing.jl (after
+# "trackgenerator.jl"); see INTEGRATION.md for the 6-line dispatch patch.  It fills the reference's OWN structs
+# (Track{BCFwd,BCBwd,DFwd,DBwd}, Segment, TrackGenerator fields), so accessors, tests and plot recipes keep working.
+#
+# NOT EXERCISED IN THIS REPOSITORY'S CI: Julia is absent from the build image.  The same ABI calls, in the same
+# order and with the same arguments, are exercised through ctypes by raytracing.jl_b200/api.py (tests/ -m gpu).
+
+const LIBRT_B200 = get(ENV, "RT_B200_LIB", "librt_b200.so")
+
+# device context per TrackGenerator, keyed by its (mutable) tracks_by_uid vector
+const _B200_CTX = IdDict{Any,Ptr{Cvoid}}()
+
+function _b200_check(ctx::Ptr{Cvoid}, rc::Cint)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:rt_last_error, LIBRT_B200), Cstring, (Ptr{Cvoid},), ctx))
+    rc == -4 && throw(DomainError("could not found track exit point."))     # trackgenerator.jl:219
+    error(msg)                                                               # carries the reference's own message
+end
+
+function _b200_context(t::TrackGenerator)
+    haskey(_B200_CTX, t.tracks_by_uid) && return _B200_CTX[t.tracks_by_uid]
+    ref = Ref{Ptr{Cvoid}}(C_NULL)
+    dev = parse(Cint, get(ENV, "RT_B200_DEVICE", "0"))
+    rc = ccall((:rt_create, LIBRT_B200), Cint, (Ptr{Ptr{Cvoid}}, Cint), ref, dev)
+    rc == 0 || error("rt_create failed: no usable CUDA device (there is no CPU fallback)")
+    ctx = ref[]
+    # ---- flatten the Gridap model: Mesh(model) already holds the two Tables and the bounding box (mesh.jl:24-31)
+    mesh = t.mesh
+    coords = get_node_coordinates(get_grid(mesh.model))          # Vector{VectorValue{2,Float64}} = contiguous x,y pairs
+    xy = reinterpret(Float64, coords)
+    cn, nc = mesh.cell_nodes, mesh.node_cells                    # Gridap Table{Int32}: .data / .ptrs, 1-based
+    bbmin = Float64[mesh.bb_min[1], mesh.bb_min[2]]
+    bbmax = Float64[mesh.bb_max[1], mesh.bb_max[2]]
+    rc = ccall((:rt_mesh_upload, LIBRT_B200), Cint,
+        (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
+        ctx, Int32(length(coords)), xy, Int32(length(cn)), Vector{Int32}(cn.ptrs), Vector{Int32}(cn.data),
+        Vector{Int32}(nc.ptrs), Vector{Int32}(nc.data), bbmin, bbmax)
+    _b200_check(ctx, rc)
+    _B200_CTX[t.tracks_by_uid] = ctx
+    finalizer(t.tracks_by_uid) do v
+        c = pop!(_B200_CTX, v, C_NULL)
+        c == C_NULL || ccall((:rt_destroy, LIBRT_B200), Cvoid, (Ptr{Cvoid},), c)
+    end
+    return ctx
+end
+
+_bc_code(bc::BoundaryType) = Int32(Int(bc))   # Vacuum=0, Reflective=1, Periodic=2 (boundary.jl:12-16)
+
+"""
+    b200_trace!(t::TrackGenerator)
+
+Device version of `trace!` (trackgenerator.jl:134-280).  The per-angle effective quadrature (the only libm
+work of the path) is computed here exactly like lines :150-166, so ϕs/δs/ωₐ are Julia's own values.
+"""
+function b200_trace!(t::TrackGenerator{T}) where {T}
+    @unpack mesh, bcs, azimuthal_quadrature, n_tracks_x, n_tracks_y, n_tracks, tracks, tracks_by_uid = t
+    @unpack δs, ϕs = azimuthal_quadrature
+    n2 = nazim2(azimuthal_quadrature)
+    δx = Vector{T}(undef, n2); δy = Vector{T}(undef, n2)
+    Δx, Δy = width(mesh), height(mesh)
+    for i in right_dir(azimuthal_quadrature)
+        ϕ = ϕs[i] = atan((Δy * n_tracks_x[i]) / (Δx * n_tracks_y[i]))
+        δx[i] = Δx / n_tracks_x[i]; δy[i] = Δy / n_tracks_y[i]; δs[i] = δx[i] * sin(ϕ)
+        j = suplementary_idx(azimuthal_quadrature, i)
+        ϕs[j] = π - ϕ; δx[j] = δx[i]; δy[j] = δy[i]; δs[j] = δs[i]
+    end
+    init_weights!(azimuthal_quadrature)
+
+    ctx = _b200_context(t)
+    codes = Int32[_bc_code(bcs.top), _bc_code(bcs.bottom), _bc_code(bcs.right), _bc_code(bcs.left)]
+    n = t.n_total_tracks
+    rc = ccall((:rt_trace, LIBRT_B200), Cint,
+        (Ptr{Cvoid}, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Int64, Int64),
+        ctx, Int32(n2), Vector{Int64}(n_tracks_x), Vector{Int64}(n_tracks_y), ϕs, sin.(ϕs), cos.(ϕs), tan.(ϕs),
+        δx, δy, codes, 1, n + 1)
+    _b200_check(ctx, rc)
+
+    azim = Vector{Int64}(undef, n); tidx = Vector{Int64}(undef, n)
+    p = Matrix{Float64}(undef, 2, n); q = Matrix{Float64}(undef, 2, n)
+    ϕ = Vector{Float64}(undef, n); ℓ = Vector{Float64}(undef, n); abc = Matrix{Float64}(undef, 3, n)
+    bcf = Vector{Int8}(undef, n); bcb = similar(bcf); df = similar(bcf); db = similar(bcf)
+    nf = Vector{Int64}(undef, n); nb = Vector{Int64}(undef, n)
+    rc = ccall((:rt_tracks_download, LIBRT_B200), Cint,
+        (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ptr{Int8}, Ptr{Int8}, Ptr{Int8}, Ptr{Int8}, Ptr{Int64}, Ptr{Int64}),
+        ctx, azim, tidx, p, q, ϕ, ℓ, abc, bcf, bcb, df, db, nf, nb)
+    _b200_check(ctx, rc)
+    for uid in 1:n
+        track = Track{BoundaryType(bcf[uid]),BoundaryType(bcb[uid]),DirectionType(df[uid]),DirectionType(db[uid])}(
+            uid, Int(azim[uid]), Int(tidx[uid]), Point2D(p[1, uid], p[2, uid]), Point2D(q[1, uid], q[2, uid]),
+            ϕ[uid], ℓ[uid], SVector(abc[1, uid], abc[2, uid], abc[3, uid]), Vector{Segment{T}}())
+        tracks_by_uid[uid] = track
+        tracks[azim[uid]][tidx[uid]] = track
+    end
+    for uid in 1:n                                           # next_tracks (trackgenerator.jl:282-348)
+        tracks_by_uid[uid].next_track_fwd = tracks_by_uid[nf[uid]]
+        tracks_by_uid[uid].next_track_bwd = tracks_by_uid[nb[uid]]
+    end
+    return t
+end
+
+"""
+    b200_segmentize!(t::TrackGenerator; k=5, rtol=√eps)
+
+Device version of `segmentize!` (trackgenerator.jl:357-369): count pass → scan → fill pass (+ fused
+`fill_volumes`), then the SoA records are materialised as the reference's `Vector{Segment}` per track.
+For meshes whose segments do not fit host memory use `rt_segments_device` / the batch callback instead.
+"""
+function b200_segmentize!(t::TrackGenerator{T}; k::Int=5, rtol::Real=Base.rtoldefault(T)) where {T}
+    @unpack tracks_by_uid, azimuthal_quadrature, volumes = t
+    !isassigned(tracks_by_uid, 1) && error("Segmentation is intended after tracing. Please, " *
+                                           "call `trace!` first!")
+    ctx = _b200_context(t)
+    nseg = Ref{Int64}(0); bad = Ref{Int64}(0); st = Ref{Int32}(0)
+    rc = ccall((:rt_segmentize, LIBRT_B200), Cint,
+        (Ptr{Cvoid}, Float64, Int32, Float64, Int32, Ptr{Float64}, UInt32, Ptr{Cvoid}, Ptr{Cvoid},
+         Ptr{Int64}, Ptr{Int64}, Ptr{Int32}),
+        ctx, Float64(t.tiny_step), Int32(k), Float64(rtol), Int32(MAX_ITER), azimuthal_quadrature.δs, UInt32(0),
+        C_NULL, C_NULL, nseg, bad, st)
+    _b200_check(ctx, rc)                                      # RT_ERR_TRACK carries the reference's error text + uid
+    n = t.n_total_tracks; S = nseg[]
+    off = Vector{Int64}(undef, n + 1)
+    _b200_check(ctx, ccall((:rt_segment_offsets, LIBRT_B200), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int32}), ctx, off, C_NULL))
+    px = Vector{Float64}(undef, S); py = similar(px); qx = similar(px); qy = similar(px); len = similar(px)
+    el = Vector{Int32}(undef, S)
+    _b200_check(ctx, ccall((:rt_segments_download, LIBRT_B200), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+        ctx, px, py, qx, qy, len, el))
+    for uid in 1:n
+        segs = tracks_by_uid[uid].segments
+        empty!(segs); sizehint!(segs, off[uid+1] - off[uid])
+        for s in off[uid]+1:off[uid+1]
+            push!(segs, Segment(Point2D(px[s], py[s]), Point2D(qx[s], qy[s]), len[s], Vector{T}(), el[s]))
+        end
+    end
+    _b200_check(ctx, ccall((:rt_volumes, LIBRT_B200), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx, volumes))
+    return t
+end

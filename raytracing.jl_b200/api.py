@@ -232,22 +232,12 @@ class _TracksByAngle:
         return nazim2(tg.azimuthal_quadrature) if self._i is None else int(tg.n_tracks[self._i - 1])
 
 
-class TrackGenerator:
-    """TrackGenerator(model, n_azim, delta; bcs, tiny_step=1e-8, volume_correction=false)
-    (src/trackgenerator.jl:80-125).  Extra keywords select the GPU and the uid shard:
-    ``device`` (CUDA ordinal) and ``shard=(rank, n_ranks)`` -- tracks are split into ``n_ranks`` contiguous uid
-    ranges of equal total track length, the mesh is replicated."""
+class TrackLayout:
+    """The pure-host part of the TrackGenerator constructor (src/trackgenerator.jl:84-108): quadrature object and
+    track counts per angle.  No device is touched; shard planning and the per-angle tables only need this."""
 
-    def __init__(self, model, n_azim: int, delta: float, bcs: BoundaryConditions | None = None, tiny_step: float = 1e-8,
-                 volume_correction: bool = False, device: int = 0, shard: tuple[int, int] = (0, 1)):
-        if isinstance(model, Mesh):
-            mesh = model
-        elif isinstance(model, UnstructuredDiscreteModel):
-            mesh = Mesh(model)
-        else:
-            raise TypeError("model must be an UnstructuredDiscreteModel")
+    def __init__(self, mesh: Mesh, n_azim: int, delta: float):
         self.mesh = mesh
-        self.bcs = bcs if bcs is not None else BoundaryConditions()
         aq = AzimuthalQuadrature(n_azim, delta)
         self.azimuthal_quadrature = aq
         n2, n4 = nazim2(aq), nazim4(aq)
@@ -265,6 +255,24 @@ class TrackGenerator:
             self.n_tracks[i - 1] = self.n_tracks[j - 1] = nx + ny
         self.n_total_tracks = int(self.n_tracks.sum())
         self._base = np.concatenate([[0], np.cumsum(self.n_tracks)]).astype(np.int64)
+
+
+class TrackGenerator(TrackLayout):
+    """TrackGenerator(model, n_azim, delta; bcs, tiny_step=1e-8, volume_correction=false)
+    (src/trackgenerator.jl:80-125).  Extra keywords select the GPU and the uid shard:
+    ``device`` (CUDA ordinal) and ``shard=(rank, n_ranks)`` -- tracks are split into ``n_ranks`` contiguous uid
+    ranges of equal total track length, the mesh is replicated."""
+
+    def __init__(self, model, n_azim: int, delta: float, bcs: BoundaryConditions | None = None, tiny_step: float = 1e-8,
+                 volume_correction: bool = False, device: int = 0, shard: tuple[int, int] = (0, 1)):
+        if isinstance(model, Mesh):
+            mesh = model
+        elif isinstance(model, UnstructuredDiscreteModel):
+            mesh = Mesh(model)
+        else:
+            raise TypeError("model must be an UnstructuredDiscreteModel")
+        super().__init__(mesh, n_azim, delta)
+        self.bcs = bcs if bcs is not None else BoundaryConditions()
         self.tiny_step = float(tiny_step)
         self.volume_correction = bool(volume_correction)
         self.volumes = np.zeros(mesh.num_cells)
@@ -412,7 +420,7 @@ class TrackGenerator:
                  str(self.volume_correction).lower()))
 
 
-def _angle_tables(tg: TrackGenerator):
+def _angle_tables(tg: TrackLayout):
     """Effective angles/spacings of trace! (src/trackgenerator.jl:150-166) with the host libm, plus the sin/cos/tan
     tables the device needs (no device trigonometry, see include/rt_b200.h)."""
     aq = tg.azimuthal_quadrature

@@ -57,9 +57,23 @@ def env_rank():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
+def broadcast_bytes(payload: bytes | None, n: int, group=None, device=None) -> bytes:
+    """Ship ``n`` bytes from rank 0 to every rank of the torch.distributed group (the NCCL unique id)."""
+    import torch
+    import torch.distributed as dist
+
+    rank = dist.get_rank(group)
+    t = torch.zeros(n, dtype=torch.uint8)
+    if rank == 0:
+        t = torch.frombuffer(bytearray(payload), dtype=torch.uint8).clone()
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda() if device is None else t.to(device)
+    dist.broadcast(t, src=0, group=group)
+    return bytes(t.cpu().numpy().tobytes())
+
+
 def init_comm(tg, group=None) -> None:
     """Create the NCCL communicator of this TrackGenerator's context across the torch.distributed group."""
-    import torch
     import torch.distributed as dist
 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -67,9 +81,11 @@ def init_comm(tg, group=None) -> None:
     buf = C.create_string_buffer(128)
     if rank == 0:
         _lib.check(tg._ctx, L.rt_comm_unique_id(tg._ctx, buf))
-    t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
-    if dist.get_backend(group) == "nccl":
-        t = t.cuda()
-    dist.broadcast(t, src=0, group=group)
-    ident = bytes(t.cpu().numpy().tobytes())
+    ident = broadcast_bytes(buf.raw if rank == 0 else None, 128, group)
     _lib.check(tg._ctx, L.rt_comm_init(tg._ctx, world, rank, ident))
+
+
+def shard_range(tg, rank: int, n_ranks: int):
+    """(uid_begin, uid_end) of ``rank``: 1-based, end exclusive."""
+    b = plan_shards(tg, n_ranks)
+    return int(b[rank]), int(b[rank + 1])

@@ -1,0 +1,119 @@
+"""CPU-side checks of the drop-in boundary: librt_b200.so loads, exports every symbol include/rt_b200.h declares,
+and fails LOUDLY (no CPU fallback) when there is no CUDA device.  No compute entry point is called without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import raytracing_jl_b200 as rt
+from raytracing_jl_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "rt_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = set(re.findall(r"\b(rt_[a-z_0-9]+)\s*\(", src))
+    names -= {"rt_batch_cb"}  # a function-pointer typedef, not an export
+    return names
+
+
+@pytest.fixture(scope="module")
+def so():
+    return rt.build()
+
+
+def test_header_and_binding_agree(so):
+    hdr = declared_symbols()
+    assert hdr == set(_lib.SYMBOLS), (hdr ^ set(_lib.SYMBOLS))
+    assert len(hdr) >= 24
+
+
+def test_library_exports_every_declared_symbol(so):
+    L = C.CDLL(so)
+    for name in declared_symbols():
+        assert hasattr(L, name), name
+    L.rt_version.restype = C.c_char_p
+    assert b"sm_100a" in L.rt_version()
+
+
+def test_library_does_not_depend_on_the_oracle(so):
+    import subprocess
+
+    deps = subprocess.run(["ldd", so], capture_output=True, text=True).stdout
+    assert "oracle" not in deps
+    pkg = os.path.join(ROOT, "raytracing.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "rt_oracle" not in txt, f
+
+
+def test_status_codes_match_header():
+    src = open(os.path.join(ROOT, "include", "rt_b200.h")).read()
+    assert re.search(r"RT_ERR_TRACK\s*=\s*-8", src) and re.search(r"RT_ERR_NO_EXIT\s*=\s*-4", src)
+    for name, val in (("RT_SEG_LITERAL", 1), ("RT_SEG_NO_VOLUMES", 2), ("RT_SEG_COUNT_ONLY", 4), ("RT_SEG_NO_CHUNKS", 8)):
+        assert re.search(rf"{name}\s*=\s*{val}\b", src) and getattr(_lib, name) == val
+    assert [int(rt.Vacuum), int(rt.Reflective), int(rt.Periodic)] == [0, 1, 2]  # src/boundary.jl:12-16
+    assert [int(rt.Forward), int(rt.Backward)] == [0, 1]  # src/track.jl:11-14
+
+
+def _has_cuda():
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_cuda(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(pincell_model):
+    h = C.c_void_p()
+    assert _lib.lib().rt_create(C.byref(h), 0) == -1  # RT_ERR_CUDA
+    with pytest.raises(rt.RTError):
+        rt.TrackGenerator(pincell_model, 8, 0.02)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "SO_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(rt.RTError):
+        _lib.lib()
+
+
+# ---- host logic that needs no device ---------------------------------------------------------------
+def test_track_layout_counts(pincell_mesh):  # test/runtests.jl:14-19
+    from tests.golden import runtests_goldens as G
+
+    lay = rt.TrackLayout(pincell_mesh, G.MAIN["n_azim"], G.MAIN["delta"])
+    assert lay.n_total_tracks == G.MAIN["n_total_tracks"]
+    assert lay.n_tracks_x.tolist() == G.MAIN["n_tracks_x"] and lay.n_tracks_y.tolist() == G.MAIN["n_tracks_y"]
+    from raytracing_jl_b200.api import _angle_tables
+
+    _angle_tables(lay)
+    aq = lay.azimuthal_quadrature
+    assert np.allclose(aq.phis, G.MAIN["phis"], rtol=1e-12) and np.allclose(aq.deltas, G.MAIN["delta_eff"], rtol=1e-12)
+    ph, w = aq.phis, aq.weights  # src/azimuthal_quad.jl:39-51 with N4 = 2
+    assert w[0] == w[3] == (ph[1] - ph[0]) / (4 * np.pi) and w[1] == w[2] == (np.pi - ph[1] - ph[0]) / (4 * np.pi)
+
+
+def test_domain_errors_are_host_side(pincell_mesh):  # src/azimuthal_quad.jl:22-25
+    for args in [(0, 0.1), (-4, 0.1), (6, 0.1), (8, 0.0), (8, -1.0)]:
+        with pytest.raises(rt.DomainError):
+            rt.TrackLayout(pincell_mesh, *args)
+
+
+def test_mesh_tables_are_gridap_layout(pincell_model, pincell_mesh):
+    ptrs, data = pincell_mesh.node_cells
+    assert ptrs[0] == 1 and ptrs[-1] == data.size + 1 and data.min() == 1 and data.max() == pincell_model.num_cells
+    for node in (1, 17, pincell_model.num_nodes):  # cells around a node in ascending cell id (Gridap get_faces(topo,0,2))
+        cells = data[ptrs[node - 1] - 1:ptrs[node] - 1]
+        assert np.all(np.diff(cells) > 0)
+        for c in cells:
+            assert node in pincell_model.cell_data[3 * (c - 1):3 * c]
+    assert pincell_mesh.bb_min.tolist() == [0.0, 0.0] and pincell_mesh.bb_max.tolist() == [1.6, 1.6]
