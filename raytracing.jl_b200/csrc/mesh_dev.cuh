@@ -20,19 +20,18 @@ struct __align__(32) EdgeRec {
     double a, b, c, len;
 };
 
-// 96-byte record of the directed half-edge h = 3*cell + k, read when a track ENTERS `cell` through its edge
-// k = (v_k, v_k+1): everything one fast transition needs in a single round trip (three 32 B sectors).
+// 32-byte record (ONE sector) of the directed half-edge h = 3*cell + k, read when a track ENTERS `cell` through its
+// edge k = (v_k, v_k+1).  The walker carries the coordinates of v_k and v_k+1 (they are the end points of the edge it
+// left the previous cell through), so the apex completes the triangle and general_form of the exit edge
+// (src/intersection.jl:57) is evaluated on the fly from the same node coordinates, in the cell's stored orientation.
 struct __align__(32) HalfEdge {
-    double ax, ay;      // apex v_k+2
-    int tw1, tw2;       // entry half-edge of the neighbour across edge k+1 = (v_k+1, apex) / k+2 = (apex, v_k),
-                        // encoded (3*cell' + k') << 1 | flip (flip: end points in opposite order); -1 on the boundary
-    float clear;        // = CellRec::clear of this cell
+    double ax, ay;  // apex v_k+2
+    int tw1, tw2;   // entry half-edge of the neighbour across edge k+1 = (v_k+1, apex) / k+2 = (apex, v_k),
+                    // encoded (3*cell' + k') << 1 | flip (flip: end points in opposite order); -1 on the boundary
+    float clear;    // = CellRec::clear of this cell
     int pad0;
-    double a1, b1, c1;  // general_form(v_k+1, apex)   (src/intersection.jl:57, the cell's stored orientation)
-    double a2, b2, c2;  // general_form(apex, v_k)
-    double pad1[2];
 };
-static_assert(sizeof(HalfEdge) == 96, "HalfEdge must be 96 bytes");
+static_assert(sizeof(HalfEdge) == 32, "HalfEdge must be 32 bytes");
 
 struct DevMesh {
     const HalfEdge *he;  // [3*cell + k]
@@ -225,7 +224,6 @@ __global__ void k_half_edges(DevMesh m, const CellRec *cells, const int *twin, H
     int c = (int)(t / 3), k = (int)(t % 3);
     int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
     const CellRec &r = cells[c];
-    const EdgeRec e1 = m.edges[3 * c + k1], e2 = m.edges[3 * c + k2];
     HalfEdge h;
     h.ax = r.vx[k2];
     h.ay = r.vy[k2];
@@ -233,14 +231,6 @@ __global__ void k_half_edges(DevMesh m, const CellRec *cells, const int *twin, H
     h.tw2 = twin[3 * c + k2];
     h.clear = INFINITY;
     h.pad0 = 0;
-    h.a1 = e1.a;
-    h.b1 = e1.b;
-    h.c1 = e1.c;
-    h.a2 = e2.a;
-    h.b2 = e2.b;
-    h.c2 = e2.c;
-    h.pad1[0] = e1.len;
-    h.pad1[1] = e2.len;
     he[t] = h;
 }
 

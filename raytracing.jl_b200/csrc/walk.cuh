@@ -161,15 +161,27 @@ __global__ void __launch_bounds__(128) k_seed(const __grid_constant__ WalkParams
     P.ch.seed_qy[cidx] = q.y;
 }
 
-// ---- 256-bit / 128-bit read-only loads and 256-bit stores (LDG.E.ENL2.256 / STG.E.ENL2.256 on sm_100a) ---------------
-__device__ __forceinline__ void ldg256(const void *p, double &a, double &b, double &c, double &d) {
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+// ---- 256-bit read-only loads / 256-bit stores (LDG.E.ENL2.256 / STG.E.ENL2.256 on sm_100a) with L2 eviction policies:
+// the half-edge table is re-read by every track that crosses a cell (keep: evict_last), the segment records are
+// written once and never read by this kernel (stream: evict_first), so the output does not flush the mesh out of L2.
+__device__ __forceinline__ unsigned long long l2_policy_keep() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
-__device__ __forceinline__ void ldg128(const void *p, double &a, double &b) {
-    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
+__device__ __forceinline__ unsigned long long l2_policy_stream() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
-__device__ __forceinline__ void stg256(void *p, double a, double b, double c, double d) {
-    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+__device__ __forceinline__ void ldg256_keep(const void *p, unsigned long long pol, double &a, double &b, double &c, double &d) {
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ void stg256_stream(void *p, unsigned long long pol, double a, double b, double c, double d) {
+    asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stg128_stream(void *p, unsigned long long pol, int a, int b, int c, int d) {
+    asm volatile("st.global.L2::cache_hint.v4.s32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "l"(pol) : "memory");
 }
 
 constexpr int kWalkThreads = 128;
@@ -200,9 +212,11 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(const __grid_constant__ W
     int prev = -1, nseg = 0, status = 0, endcode = END_TRACK;
     double sum = 0.0;
     long long out = 0;
-    // fast state: last pushed cell, the half-edge through which the next cell is entered (-1: boundary), the
-    // signed distances of that edge's end points from the track line (in the half-edge's order), the exit point
+    // fast state: last pushed cell, the half-edge through which the next cell is entered (-1: boundary), the end
+    // points (u, w) of that edge in the half-edge's order with their signed distances (sp, sq) from the track line,
+    // and the exit point
     int cur = -1, hB = -1;
+    double ux = 0, uy = 0, wx = 0, wy = 0;
     double sp = 0, sq = 0, qx = 0, qy = 0, clearA = INFINITY;
     bool clean = false;
     int stop_cell = -1;  // count pass: hand-off cell of the next valid chunk
@@ -211,6 +225,8 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(const __grid_constant__ W
     unsigned long long cnt[4] = {0, 0, 0, 0};
     const bool literal_only = (P.flags & 1u) != 0;
     bool active = false;
+    const unsigned long long pol_keep = l2_policy_keep();
+    const unsigned long long pol_stream = FILL ? l2_policy_stream() : 0ull;
 
     // arm the fast path after cell e was pushed with exit edge e_q (local index) and exit point (ex, ey)
     auto arm = [&](int e, int e_q, double ex, double ey) {
@@ -223,14 +239,18 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(const __grid_constant__ W
 #pragma unroll
         for (int q = 0; q < 3; ++q) s[q] = trk.a * r.vx[q] + trk.b * r.vy[q] + trk.c;
         double thr = g * clearA;
-        double sa = e_q == 0 ? s[0] : (e_q == 1 ? s[1] : s[2]);
-        double sb = e_q == 0 ? s[1] : (e_q == 1 ? s[2] : s[0]);
+        int e_n = e_q == 2 ? 0 : e_q + 1;
+        double sa = s[e_q], sb = s[e_n];
         clean = (fabs(s[0]) >= thr) && (fabs(s[1]) >= thr) && (fabs(s[2]) >= thr) && ((sa > 0) != (sb > 0));
         int enc = m.twin[3 * e + e_q];
         hB = enc < 0 ? -1 : (enc >> 1);
         bool flip = (enc & 1) != 0;
         sp = flip ? sb : sa;
         sq = flip ? sa : sb;
+        ux = flip ? r.vx[e_n] : r.vx[e_q];
+        uy = flip ? r.vy[e_n] : r.vy[e_q];
+        wx = flip ? r.vx[e_q] : r.vx[e_n];
+        wy = flip ? r.vy[e_q] : r.vy[e_n];
     };
 
     if (t < P.n_tracks && t >= P.trk_begin && t < P.trk_end) {
@@ -302,10 +322,10 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(const __grid_constant__ W
                     double *dst[5] = {P.opx, P.opy, P.oqx, P.oqy, P.olen};
 #pragma unroll
                     for (int a = 0; a < 5; ++a)
-                        stg256(dst[a] + g0, s_buf[(a * 4 + 0) * kWalkThreads + tid], s_buf[(a * 4 + 1) * kWalkThreads + tid],
-                               s_buf[(a * 4 + 2) * kWalkThreads + tid], s_buf[(a * 4 + 3) * kWalkThreads + tid]);
-                    *reinterpret_cast<int4 *>(P.oelem + g0) = make_int4(s_el[0 * kWalkThreads + tid], s_el[1 * kWalkThreads + tid],
-                                                                        s_el[2 * kWalkThreads + tid], s_el[3 * kWalkThreads + tid]);
+                        stg256_stream(dst[a] + g0, pol_stream, s_buf[(a * 4 + 0) * kWalkThreads + tid], s_buf[(a * 4 + 1) * kWalkThreads + tid],
+                                      s_buf[(a * 4 + 2) * kWalkThreads + tid], s_buf[(a * 4 + 3) * kWalkThreads + tid]);
+                    stg128_stream(P.oelem + g0, pol_stream, s_el[0 * kWalkThreads + tid], s_el[1 * kWalkThreads + tid],
+                                  s_el[2 * kWalkThreads + tid], s_el[3 * kWalkThreads + tid]);
                 } else {
                     for (int kk = kf; kk <= k; ++kk) {
                         P.opx[g0 + kk] = s_buf[(0 * 4 + kk) * kWalkThreads + tid];
@@ -338,32 +358,28 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(const __grid_constant__ W
             if (mode != MODE_FAST) continue;
             bool ok = false;
             if (hB >= 0 && clean) {
-                const HalfEdge *hp = m.he + hB;
-                double ax, ay, w0, w1, a1, b1, c1, a2, b2, c2;
-                ldg256(hp, ax, ay, w0, w1);
-                ldg256(reinterpret_cast<const char *>(hp) + 32, a1, b1, c1, a2);
-                ldg128(reinterpret_cast<const char *>(hp) + 64, b2, c2);
+                double ax, ay, w0, w1;
+                ldg256_keep(m.he + hB, pol_keep, ax, ay, w0, w1);
                 int tw1 = __double2loint(w0), tw2 = __double2hiint(w0);
                 float clearf = __int_as_float(__double2loint(w1));
                 double sa = trk.a * ax + trk.b * ay + trk.c;
                 double clearB = fabs((double)clearf);
                 double thr = g * fmax(clearA, clearB);
                 bool clear_ok = (fabs(sa) >= thr) && (fabs(sp) >= thr) && (fabs(sq) >= thr);
-                // the entry edge (v_k, v_k+1) is crossed (sp, sq of opposite sign); the exit is the other edge whose
-                // non-apex end lies on the opposite side of the apex: edge k+1 = (v_k+1, apex) or k+2 = (apex, v_k)
+                // the entry edge (v_k, v_k+1) = (u, w) is crossed (sp, sq of opposite sign); the exit is the other edge whose
+                // non-apex end lies on the opposite side of the apex: edge k+1 = (w, apex) or k+2 = (apex, u)
                 bool exit1 = (sa > 0) != (sq > 0);
-                int cellB = hB / 3;
-                int kin = hB - 3 * cellB;
                 if (clear_ok) {
-                    Line L;
-                    L.a = exit1 ? a1 : a2;
-                    L.b = exit1 ? b1 : b2;
-                    L.c = exit1 ? c1 : c2;
+                    // general_form(P_i, P_j) of the exit edge in the cell's stored orientation, src/intersection.jl:11-18,57
+                    P2 xi{exit1 ? wx : ax, exit1 ? wy : ay}, xo{exit1 ? ax : ux, exit1 ? ay : uy};
+                    Line L = general_form(xi, xo);
                     P2 X;
                     bool par = intersection(trk, L, X);  // same formula as src/intersection.jl:127-138
                     if (!par) {
                         P2 Xin{qx, qy};
                         // int_points are stored in edge-index order; order_intersection_points picks the first
+                        int cellB = hB / 3;
+                        int kin = hB - 3 * cellB;
                         bool kin_lt_kout = (kin == 0) || (kin == 1 && exit1);
                         bool in_first = kin_lt_kout ? order_first(right, Xin, X) : !order_first(right, X, Xin);
                         double l = norm2(qx - X.x, qy - X.y);  // Segment(p, q): norm(p - q), src/segment.jl:32
@@ -373,10 +389,14 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(const __grid_constant__ W
                         if (accept) {
                             double pxx = qx, pyy = qy;
                             int enc = exit1 ? tw1 : tw2;
-                            double na = exit1 ? sq : sa, nb = exit1 ? sa : sp;  // s at the exit edge's ordered end points
+                            double si = exit1 ? sq : sa, so = exit1 ? sa : sp;  // s at the exit edge's ordered end points
                             bool flip = (enc & 1) != 0;
-                            sp = flip ? nb : na;
-                            sq = flip ? na : nb;
+                            sp = flip ? so : si;
+                            sq = flip ? si : so;
+                            ux = flip ? xo.x : xi.x;
+                            uy = flip ? xo.y : xi.y;
+                            wx = flip ? xi.x : xo.x;
+                            wy = flip ? xi.y : xo.y;
                             hB = enc < 0 ? -1 : (enc >> 1);
                             cur = cellB;
                             qx = X.x;
