@@ -155,8 +155,13 @@ int rt_stats(rt_ctx *ctx, double stats[8]);
  * 3 scan, 4 fill, 5 volumes(+allreduce) */
 int rt_phase_ms(rt_ctx *ctx, double ms[6]);
 
+/* self-test: 64*n_threads random quotients x/d (exponents within +-exp_span of 1.0, zeros, powers of two, all-ones
+ * mantissas) through the shared-reciprocal division the walk kernels use, compared bit for bit with the IEEE `/`. */
+int rt_selftest_division(rt_ctx *ctx, int64_t n_threads, uint64_t seed, int32_t exp_span, int64_t *mismatches);
+
 /* tuning knobs: "chunk_segments" (minimum expected segments per sub-track chunk, default 64),
- * "target_walkers" (chunks are sized so that about this many walkers exist, default 148*2048*4) */
+ * "target_walkers" (chunks are sized so that about this many walkers exist, default 148*2048*4),
+ * "order_grid" (G: walkers are launched in Morton order of a G x G tiling of the domain, default 16, 0 = uid order) */
 int rt_set_option(rt_ctx *ctx, const char *name, double value);
 /* CUDA-event stopwatch on the context's launching stream (bench harness: torch.cuda.Event cannot see it). */
 int rt_timer_start(rt_ctx *ctx);

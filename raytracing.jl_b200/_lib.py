@@ -13,7 +13,7 @@ import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-SO_PATH = os.path.join(_PKG, "librt_b200.so")
+SO_PATH = os.environ.get("RT_B200_LIB") or os.path.join(_PKG, "librt_b200.so")  # RT_B200_LIB: an alternative build
 _CSRC = os.path.join(_PKG, "csrc")
 _SOURCES = ["rt_b200.cu", "geom.cuh", "mesh_dev.cuh", "walk.cuh", "trace.cuh", "scan.cuh"]
 
@@ -82,6 +82,7 @@ SYMBOLS = {
     "rt_stats": (C.c_int, [_vp, _f64]),
     "rt_phase_ms": (C.c_int, [_vp, _f64]),
     "rt_set_option": (C.c_int, [_vp, C.c_char_p, C.c_double]),
+    "rt_selftest_division": (C.c_int, [_vp, C.c_int64, C.c_uint64, C.c_int32, C.POINTER(C.c_int64)]),
     "rt_timer_start": (C.c_int, [_vp]),
     "rt_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_double)]),
 }

@@ -27,7 +27,7 @@ struct __align__(32) EdgeRec {
 struct __align__(32) HalfEdge {
     double ax, ay;  // apex v_k+2
     int tw1, tw2;   // entry half-edge of the neighbour across edge k+1 = (v_k+1, apex) / k+2 = (apex, v_k),
-                    // encoded (3*cell' + k') << 1 | flip (flip: end points in opposite order); -1 on the boundary
+                    // encoded (3*cell' + k') << 3 | k' << 1 | flip (flip: end points in opposite order); -1 on the boundary
     float clear;    // = CellRec::clear of this cell
     int pad0;
 };
@@ -211,8 +211,8 @@ __global__ void k_twins(int n_cells, const int *cell_nodes, const int *nbr, int 
         const int *nn = &cell_nodes[3 * n1];
         for (int kk = 0; kk < 3; ++kk) {
             int a2 = nn[kk], b2 = nn[(kk + 1) % 3];
-            if (a2 == b && b2 == a) enc = ((3 * n1 + kk) << 1) | 1;  // opposite order (consistently oriented pair)
-            if (a2 == a && b2 == b) enc = ((3 * n1 + kk) << 1) | 0;
+            if (a2 == b && b2 == a) enc = ((3 * n1 + kk) << 3) | (kk << 1) | 1;  // opposite order (consistently oriented pair)
+            if (a2 == a && b2 == b) enc = ((3 * n1 + kk) << 3) | (kk << 1) | 0;
         }
     }
     twin[t] = enc;
@@ -291,7 +291,7 @@ __device__ __forceinline__ void kbest_insert(KBest &s, double d2, int id) {
 // Exact k nearest nodes of (x, y) (ties: lowest node id), skipping node `skip` -- what the reference asks of
 // nn(kdtree, x) (src/mesh.jl:107) and knn(kdtree, x, k, true, skip) (src/mesh.jl:123). Ring search: after ring r every
 // unvisited node is farther than the distance to the border of the visited block.
-__device__ __noinline__ void knn_query(const DevMesh &m, double x, double y, int skip, KBest &s) {
+__device__ RT_SLOWPATH_INLINE void knn_query(const DevMesh &m, double x, double y, int skip, KBest &s) {
     s.n = 0;
     int bx = (int)floor((x - m.g0x) * m.ginv);
     int by = (int)floor((y - m.g0y) * m.ginv);
@@ -353,7 +353,7 @@ __device__ __forceinline__ int scan_node_cells(const DevMesh &m, int node, doubl
 }
 
 // find_element(mesh, x, k)  src/mesh.jl:103-146 ; returns 0-based cell or -1
-__device__ __noinline__ int find_element(const DevMesh &m, double x, double y, int k, unsigned long long *nq) {
+__device__ RT_SLOWPATH_INLINE int find_element(const DevMesh &m, double x, double y, int k, unsigned long long *nq) {
     KBest s;
     s.k = 1;
     knn_query(m, x, y, -1, s);
@@ -380,7 +380,7 @@ __device__ __forceinline__ bool inboundary(const DevMesh &m, double x, double y,
 
 // intersections(mesh, cell, track)  src/intersection.jl:34-119 (triangles: 3 edges, at most 3 hits).
 // Returns 0, or 4 (RT_TRACK_UNDEF) when the 3-hit selection never assigns x_int1. e_p/e_q: local edges of p and q.
-__device__ __noinline__ int intersections(const DevMesh &m, int cell, const Line &trk, bool phi_lt_half_pi, P2 &p, P2 &q,
+__device__ RT_SLOWPATH_INLINE int intersections(const DevMesh &m, int cell, const Line &trk, bool phi_lt_half_pi, P2 &p, P2 &q,
                                           int &e_p, int &e_q) {
     const CellRec &r = m.cells[cell];
     P2 ip[3];

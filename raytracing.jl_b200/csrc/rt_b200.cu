@@ -72,6 +72,8 @@ struct rt_ctx {
     bool segmented = false;
     DevBuf b_count, b_status, b_offsets, b_tile, b_vol, b_voln, b_counters, b_bad;
     DevBuf b_nch, b_blk_chunks, b_unit_base, b_unit_block, b_ch_i, b_ch_d;  // chunk plan (walk.cuh ChunkPlan)
+    DevBuf b_order, b_okeys, b_ohist;  // spatial execution order of the units
+    int opt_order_grid = 16;           // G x G tiles (0: identity order)
     long long n_units = 0;
     double opt_chunk_segments = 64.0;               // minimum expected segments per chunk
     double opt_target_walkers = 148.0 * 2048.0 * 4.0;  // chunks are sized so that about this many walkers exist
@@ -173,7 +175,8 @@ extern "C" void rt_destroy(rt_ctx *ctx) {
                      &ctx->b_err,     &ctx->b_count,      &ctx->b_status,   &ctx->b_offsets, &ctx->b_tile,    &ctx->b_vol,
                      &ctx->b_voln,    &ctx->b_counters,   &ctx->b_bad,      &ctx->b_seg_d,   &ctx->b_seg_e,
                      &ctx->b_twin,    &ctx->b_he,         &ctx->b_node_reach,
-                     &ctx->b_nch,     &ctx->b_blk_chunks, &ctx->b_unit_base, &ctx->b_unit_block, &ctx->b_ch_i, &ctx->b_ch_d};
+                     &ctx->b_nch,     &ctx->b_blk_chunks, &ctx->b_unit_base, &ctx->b_unit_block, &ctx->b_ch_i, &ctx->b_ch_d,
+                     &ctx->b_order,   &ctx->b_okeys,      &ctx->b_ohist};
     for (DevBuf *b : all) release(*b);
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
     if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
@@ -721,6 +724,24 @@ extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rt
         P.unit_end = n_units;
         ctx->n_units = n_units;
         launches += 5;
+        // ---- spatial execution order (counting sort of the units by Morton tile)
+        ch.order = nullptr;
+        if (ctx->opt_order_grid > 0 && n_units < (1LL << 31)) {
+            int G = std::min(ctx->opt_order_grid, 256);
+            int gp = 1;
+            while (gp < G) gp <<= 1;
+            size_t n_keys = (size_t)gp * gp;
+            CK(ensure(ctx->b_order, sizeof(int) * (size_t)n_units));
+            CK(ensure(ctx->b_okeys, sizeof(int) * (size_t)n_units));
+            CK(ensure(ctx->b_ohist, sizeof(int) * (3 * n_keys + 1)));
+            int *hist = (int *)ctx->b_ohist.p, *ptrs = hist + n_keys, *cursor = ptrs + n_keys + 1;
+            CK(cudaMemsetAsync(hist, 0, sizeof(int) * (3 * n_keys + 1), st));
+            k_unit_keys<<<blocks_for(n_units, 256), 256, 0, st>>>(P, G, (int *)ctx->b_okeys.p, hist);
+            CK((exclusive_scan<int, int>(ctx, hist, ptrs, (long long)n_keys)));
+            k_unit_scatter<<<blocks_for(n_units, 256), 256, 0, st>>>(n_units, (const int *)ctx->b_okeys.p, ptrs, cursor, (int *)ctx->b_order.p);
+            ch.order = (const int *)ctx->b_order.p;
+            launches += 5;
+        }
         // ---- seeds, count pass, per-track fix-up
         P.vol = nullptr;
         k_seed<<<blocks_for(n_units * 32, 128), 128, 0, st>>>(P);
@@ -791,7 +812,8 @@ extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rt
             P.trk_begin = b;
             P.trk_end = e;
             P.offset_base = total > cap ? h_off[b] : 0;
-            if (total > cap) {  // the warp units of the 32-track blocks overlapping [b, e)
+            if (total > cap) {  // the warp units of the 32-track blocks overlapping [b, e), in identity order
+                P.ch.order = nullptr;
                 P.unit_begin = h_unit_base[(size_t)(b >> 5)];
                 P.unit_end = h_unit_base[(size_t)((e - 1) >> 5) + 1];
             }
@@ -945,6 +967,62 @@ extern "C" int rt_volumes(rt_ctx *ctx, double *volumes) {
     return RT_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// self-test: the shared-reciprocal division of geom.cuh must equal the IEEE `/` bit for bit
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long &x) {
+    unsigned long long z = (x += 0x9e3779b97f4a7c15ull);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+__global__ void k_selftest_division(long long n, unsigned long long seed, int exp_span, unsigned long long *mismatch) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long st = seed + 0x632be59bd9b4e019ull * (unsigned long long)(i + 1);
+    unsigned long long bad = 0;
+    for (int rep = 0; rep < 64; ++rep) {
+        // denominators and numerators with random sign, random mantissa and an exponent within +-exp_span of 1.0; every 16th
+        // numerator is an exact zero / a power of two / has an all-ones mantissa (the classical hard cases)
+        unsigned long long r1 = splitmix64(st), r2 = splitmix64(st), r3 = splitmix64(st);
+        int e1 = 1023 + (int)(r3 % (2 * exp_span + 1)) - exp_span, e2 = 1023 + (int)((r3 >> 20) % (2 * exp_span + 1)) - exp_span;
+        e1 = min(max(e1, 0), 2046);
+        e2 = min(max(e2, 1), 2046);
+        unsigned long long mx = r1 & 0xfffffffffffffull, mn = r2 & 0xfffffffffffffull;
+        int kind = (int)((r3 >> 44) & 15);
+        if (kind == 1) mx = 0;
+        if (kind == 2) mx = 0xfffffffffffffull;
+        if (kind == 3) mn = 0xfffffffffffffull;
+        if (kind == 4) mn = 0;
+        double x = __longlong_as_double((long long)(((r1 >> 63) << 63) | ((unsigned long long)e1 << 52) | mx));
+        double d = __longlong_as_double((long long)(((r2 >> 63) << 63) | ((unsigned long long)e2 << 52) | mn));
+        if (kind == 5) x = 0.0;
+        if (kind == 6) x = -0.0;
+        Recip r = recip_prepare(d);
+        double q1 = div_shared(x, r), q2 = x / d;
+        if (__double_as_longlong(q1) != __double_as_longlong(q2)) bad++;
+    }
+    if (bad) atomicAdd(mismatch, bad);
+}
+
+extern "C" int rt_selftest_division(rt_ctx *ctx, int64_t n_threads, uint64_t seed, int32_t exp_span, int64_t *mismatches) {
+    if (!ctx || !mismatches || n_threads < 1 || exp_span < 0 || exp_span > 1022) return RT_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    DevBuf d;
+    CK(ensure(d, sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(d.p, 0, sizeof(unsigned long long), ctx->stream));
+    k_selftest_division<<<blocks_for(n_threads, 256), 256, 0, ctx->stream>>>(n_threads, seed, exp_span, (unsigned long long *)d.p);
+    CK(cudaGetLastError());
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, d.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    release(d);
+    *mismatches = (int64_t)h;
+    return RT_OK;
+}
+
 extern "C" int rt_stats(rt_ctx *ctx, double stats[8]) {
     if (!ctx || !stats) return RT_ERR_ARG;
     memcpy(stats, ctx->stats, sizeof(ctx->stats));
@@ -982,6 +1060,8 @@ extern "C" int rt_set_option(rt_ctx *ctx, const char *name, double value) {
         ctx->opt_chunk_segments = value;
     else if (n == "target_walkers" && value >= 1.0)
         ctx->opt_target_walkers = value;
+    else if (n == "order_grid" && value >= 0.0 && value <= 256.0)
+        ctx->opt_order_grid = (int)value;
     else
         return fail(ctx, RT_ERR_ARG, "rt_set_option: unknown option or bad value: %s", name);
     return RT_OK;

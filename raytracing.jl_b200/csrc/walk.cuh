@@ -38,6 +38,7 @@ struct ChunkPlan {
     int *unit_block;        // per warp-unit: which block of 32 consecutive tracks
     long long *unit_base;   // per block: first unit; [n_blocks] = n_units
     long long n_units;
+    const int *order;       // execution order of the units (spatially sorted), or nullptr = identity
     int *seed_cell;         // >= 0: valid seed (cell already pushed by the previous walker); -1: void
     int *seed_kexit;
     double *seed_qx, *seed_qy;
@@ -94,6 +95,47 @@ __global__ void k_fill_units(long long n_blocks, const long long *unit_base, int
     for (long long u = unit_base[b]; u < unit_base[b + 1]; ++u) unit_block[u] = (int)b;
 }
 
+
+// ---- spatial execution order of the units ------------------------------------------------------------------------------
+// Units (= warps) are independent, so their launch order is free.  Sorting them by the Morton index of the G x G tile
+// that holds the chunk's mid point makes the walkers that are resident at the same time work on the same part of the
+// mesh: the half-edge records they gather then hit in L1/L2 instead of HBM (the whole table does not fit the cache).
+__device__ __forceinline__ unsigned morton2(unsigned x, unsigned y) {
+    auto spread = [](unsigned v) {
+        v = (v | (v << 8)) & 0x00ff00ffu;
+        v = (v | (v << 4)) & 0x0f0f0f0fu;
+        v = (v | (v << 2)) & 0x33333333u;
+        v = (v | (v << 1)) & 0x55555555u;
+        return v;
+    };
+    return spread(x) | (spread(y) << 1);
+}
+
+__global__ void k_unit_keys(const __grid_constant__ WalkParams P, int G, int *keys, int *hist) {
+    long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (u >= P.ch.n_units) return;
+    int b = P.ch.unit_block[u];
+    int j = (int)(u - P.ch.unit_base[b]);
+    long long t = min(32LL * b + 16, P.n_tracks - 1);
+    int n = P.ch.nch[t];
+    int jj = min(j, n - 1);
+    int az = P.t.azim[t];
+    double s = P.t.len[t] * (((double)jj + 0.5) / (double)n);
+    double x = P.t.px[t] + s * P.ang.cosp[az], y = P.t.py[t] + s * P.ang.sinp[az];
+    double fx = (x - P.m.bbmin[0]) / (P.m.bbmax[0] - P.m.bbmin[0]), fy = (y - P.m.bbmin[1]) / (P.m.bbmax[1] - P.m.bbmin[1]);
+    int ix = min(max((int)(fx * G), 0), G - 1), iy = min(max((int)(fy * G), 0), G - 1);
+    int key = (int)morton2((unsigned)ix, (unsigned)iy);
+    keys[u] = key;
+    atomicAdd(&hist[key], 1);
+}
+
+__global__ void k_unit_scatter(long long n_units, const int *keys, const int *ptrs, int *cursor, int *order) {
+    long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    int key = keys[u];
+    order[ptrs[key] + atomicAdd(&cursor[key], 1)] = (int)u;
+}
+
 struct TrackCtx {
     Line trk;
     double g, sx, sy, tlen, delta;
@@ -115,8 +157,9 @@ __device__ __forceinline__ double bbox_dist(const DevMesh &m, double x, double y
 __global__ void __launch_bounds__(128) k_seed(const __grid_constant__ WalkParams P) {
     long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
-    long long unit = P.unit_begin + gw;
-    if (unit >= P.unit_end) return;
+    long long slot = P.unit_begin + gw;
+    if (slot >= P.unit_end) return;
+    long long unit = P.ch.order ? P.ch.order[slot] : slot;
     const DevMesh &m = P.m;
     int b = P.ch.unit_block[unit];
     int j = (int)(unit - P.ch.unit_base[b]);
@@ -185,10 +228,94 @@ __device__ __forceinline__ void stg128_stream(void *p, unsigned long long pol, i
 }
 
 constexpr int kWalkThreads = 128;
+// resident blocks per SM the register allocator must allow (without it ptxas picks ~56-72 registers and spills the walk state)
+#ifndef RT_WALK_MIN_BLOCKS
+#define RT_WALK_MIN_BLOCKS 4
+#endif
+
+// ---- the literal walk: src/track.jl:119-168 iterated until ONE segment is pushed (or the walk ends) ------------------
+struct LitIn {
+    double a, b, c;   // track.ABC
+    double sx, sy;    // tiny_step * (cos phi, sin phi)
+    double x, y;      // xp = advance_step(x, tiny, phi) is the first point examined
+    int prev;         // prev_element (-1: none)
+    bool right;       // isless(phi, pi/2)
+    bool at_start;    // isempty(segments) and this walker owns the track start
+};
+struct LitOut {
+    int code;    // 0: pushed a segment, END_TRACK, END_ERROR
+    int status;  // RT_TRACK_* when code == END_ERROR
+    int e, e_q;  // pushed cell, local exit edge (-1: no single exit edge)
+    double px, py, qx, qy, l;
+    unsigned iters;
+    unsigned long long nq[2];  // nearest-node / knn queries
+};
+
+__device__ RT_LITERAL_CALL void literal_until_push(const WalkParams &P, const LitIn &in, LitOut &out) {
+    const DevMesh &m = P.m;
+    Line trk{in.a, in.b, in.c};
+    double xpx = in.x + in.sx, xpy = in.y + in.sy;  // advance_step, src/point.jl:43 / src/track.jl:114,165
+    int prev = in.prev;
+    out.code = END_ERROR;
+    out.status = 0;
+    out.e = out.e_q = -1;
+    out.iters = 0;
+    out.nq[0] = out.nq[1] = 0;
+    while (true) {
+        if (++out.iters > (unsigned)kRunaway) {
+            out.status = 3;
+            return;
+        }
+        // find_element's result is discarded on boundary steps (src/track.jl:122-134): test the boundary first
+        if (inboundary(m, xpx, xpy, P.tiny)) {
+            if (in.at_start) {
+                xpx = xpx + in.sx;
+                xpy = xpy + in.sy;
+                continue;
+            }
+            out.code = END_TRACK;
+            return;
+        }
+        int e = find_element(m, xpx, xpy, 2, out.nq);
+        if (e < 0) {
+            e = find_element(m, xpx, xpy, P.k, out.nq);
+            if (e < 0) {
+                out.status = 1;  // "Try increasing `k`", src/track.jl:141
+                return;
+            }
+        }
+        if (e == prev) {
+            xpx = xpx + in.sx;
+            xpy = xpy + in.sy;
+            continue;
+        }
+        P2 p, q;
+        int e_p, e_q;
+        int rc = intersections(m, e, trk, in.right, p, q, e_p, e_q);
+        if (rc) {
+            out.status = rc;
+            return;
+        }
+        if (isapprox_pt(p, q)) {  // src/track.jl:156-159
+            xpx = xpx + in.sx;
+            xpy = xpy + in.sy;
+            continue;
+        }
+        out.code = 0;
+        out.e = e;
+        out.e_q = e_q;
+        out.px = p.x;
+        out.py = p.y;
+        out.qx = q.x;
+        out.qy = q.y;
+        out.l = norm2(p.x - q.x, p.y - q.y);
+        return;
+    }
+}
 
 // ---- the walk ----------------------------------------------------------------------------------------------
 template <bool FILL>
-__global__ void __launch_bounds__(kWalkThreads) k_walk(const __grid_constant__ WalkParams P) {
+__global__ void __launch_bounds__(kWalkThreads, RT_WALK_MIN_BLOCKS) k_walk(const __grid_constant__ WalkParams P) {
     const unsigned FULL = 0xffffffffu;
     const DevMesh &m = P.m;
     // fill pass: every thread stages 4 consecutive segments and writes them as full, aligned 32-byte sectors
@@ -197,32 +324,32 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(const __grid_constant__ W
     const int tid = threadIdx.x;
     long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
-    long long unit = P.unit_begin + gw;
-    if (unit >= P.unit_end) return;  // whole warp
+    long long slot = P.unit_begin + gw;
+    if (slot >= P.unit_end) return;  // whole warp
+    long long unit = P.ch.order ? P.ch.order[slot] : slot;
     int blk = P.ch.unit_block[unit];
     int j = (int)(unit - P.ch.unit_base[blk]);
     long long t = 32LL * blk + lane;
     long long cidx = unit * 32 + lane;
 
     int mode = MODE_DONE;
-    Line trk{0, 0, 0};
-    double sx = 0, sy = 0, g = 0, delta = 0;
+    double ta = 0, tb = 0, tc = 0, g = 0;
+    int az = 0;
     bool right = true;
-    double xpx = 0, xpy = 0;  // literal walk position
-    int prev = -1, nseg = 0, status = 0, endcode = END_TRACK;
+    int nseg = 0, status = 0, endcode = END_TRACK;
     double sum = 0.0;
     long long out = 0;
-    // fast state: last pushed cell, the half-edge through which the next cell is entered (-1: boundary), the end
-    // points (u, w) of that edge in the half-edge's order with their signed distances (sp, sq) from the track line,
-    // and the exit point
-    int cur = -1, hB = -1;
-    double ux = 0, uy = 0, wx = 0, wy = 0;
-    double sp = 0, sq = 0, qx = 0, qy = 0, clearA = INFINITY;
-    bool clean = false;
+    // fast state: last pushed cell `cur` with exit point (qx, qy); the encoded half-edge `enc` through which the next
+    // cell is entered (-1: boundary); the two end points of that edge (e1, e2) with their signed distances (s1, s2) from
+    // the track line; f: e1 is the half-edge's SECOND vertex v_k+1 (else its first, v_k)
+    int cur = -1, enc = -1;
+    bool f = false, clean = false;
+    double e1x = 0, e1y = 0, e2x = 0, e2y = 0, s1 = 0, s2 = 0, qx = 0, qy = 0;
+    float clearA = INFINITY;
+    double rax = 0, ray = 0, rw0 = 0, rw1 = 0;  // the (prefetched) record of half-edge `enc`
     int stop_cell = -1;  // count pass: hand-off cell of the next valid chunk
     int limit = P.max_iter;
-    long long slow_iters = 0;
-    unsigned long long cnt[4] = {0, 0, 0, 0};
+    int n_litpush = 0;  // segments pushed by the literal path (the others are fast transitions)
     const bool literal_only = (P.flags & 1u) != 0;
     bool active = false;
     const unsigned long long pol_keep = l2_policy_keep();
@@ -234,23 +361,20 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(const __grid_constant__ W
         cur = e;
         qx = ex;
         qy = ey;
-        clearA = fabs((double)r.clear);
-        double s[3];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) s[q] = trk.a * r.vx[q] + trk.b * r.vy[q] + trk.c;
-        double thr = g * clearA;
+        clearA = fabsf(r.clear);
+        double v0 = ta * r.vx[0] + tb * r.vy[0] + tc, v1 = ta * r.vx[1] + tb * r.vy[1] + tc, v2 = ta * r.vx[2] + tb * r.vy[2] + tc;
+        double thr = g * (double)clearA;
         int e_n = e_q == 2 ? 0 : e_q + 1;
-        double sa = s[e_q], sb = s[e_n];
-        clean = (fabs(s[0]) >= thr) && (fabs(s[1]) >= thr) && (fabs(s[2]) >= thr) && ((sa > 0) != (sb > 0));
-        int enc = m.twin[3 * e + e_q];
-        hB = enc < 0 ? -1 : (enc >> 1);
-        bool flip = (enc & 1) != 0;
-        sp = flip ? sb : sa;
-        sq = flip ? sa : sb;
-        ux = flip ? r.vx[e_n] : r.vx[e_q];
-        uy = flip ? r.vy[e_n] : r.vy[e_q];
-        wx = flip ? r.vx[e_q] : r.vx[e_n];
-        wy = flip ? r.vy[e_q] : r.vy[e_n];
+        s1 = e_q == 0 ? v0 : (e_q == 1 ? v1 : v2);
+        s2 = e_q == 0 ? v1 : (e_q == 1 ? v2 : v0);
+        clean = (fabs(v0) >= thr) && (fabs(v1) >= thr) && (fabs(v2) >= thr) && ((s1 > 0) != (s2 > 0));
+        e1x = r.vx[e_q];
+        e1y = r.vy[e_q];
+        e2x = r.vx[e_n];
+        e2y = r.vy[e_n];
+        enc = m.twin[3 * e + e_q];
+        f = (enc & 1) != 0;  // (e1, e2) is the neighbour's (v_k, v_k+1) unless the twin runs in the opposite order
+        if (enc >= 0) ldg256_keep(m.he + (enc >> 3), pol_keep, rax, ray, rw0, rw1);
     };
 
     if (t < P.n_tracks && t >= P.trk_begin && t < P.trk_end) {
@@ -262,26 +386,20 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(const __grid_constant__ W
             active = limit > 0;
         }
         if (active) {
-            int az = P.t.azim[t];
-            trk.a = P.t.a[t];
-            trk.b = P.t.b[t];
-            trk.c = P.t.c[t];
+            az = P.t.azim[t];
+            ta = P.t.a[t];
+            tb = P.t.b[t];
+            tc = P.t.c[t];
             double phi = P.ang.phi[az];
             right = phi < kPi / 2;         // isless(phi, pi/2), src/intersection.jl:153
-            sx = P.tiny * P.ang.cosp[az];  // advance_step: x + step*Point2D(cos phi, sin phi), src/point.jl:43
-            sy = P.tiny * P.ang.sinp[az];
-            delta = P.vol ? P.ang.delta_eff[az] : 0.0;
-            g = sqrt(trk.a * trk.a + trk.b * trk.b);
+            g = sqrt(ta * ta + tb * tb);
             if (FILL) out = P.offsets[t] - P.offset_base + P.ch.prefix[cidx];
             if (j == 0) {
-                xpx = P.t.px[t] + sx;  // src/track.jl:114
-                xpy = P.t.py[t] + sy;
+                qx = P.t.px[t];  // the literal walk starts from advance_step(track.p), src/track.jl:114
+                qy = P.t.py[t];
                 mode = MODE_SLOW;
             } else {
                 arm(seed, P.ch.seed_kexit[cidx], P.ch.seed_qx[cidx], P.ch.seed_qy[cidx]);  // k_seed verified `clean`
-                prev = cur;
-                xpx = qx + sx;
-                xpy = qy + sy;
                 mode = (literal_only || !clean) ? MODE_SLOW : MODE_FAST;
             }
             if (!FILL) {
@@ -338,7 +456,7 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(const __grid_constant__ W
                 }
             }
         }
-        if (P.vol) atomicAdd(&P.vol[e], delta * l);  // volumes[i] += delta_s[a]*l, src/trackgenerator.jl:382
+        if (P.vol) atomicAdd(&P.vol[e], P.ang.delta_eff[az] * l);  // volumes[i] += delta_s[a]*l, src/trackgenerator.jl:382
         sum += l;
         nseg += 1;
         if (nseg >= limit) {  // while i < MAX_ITER (src/track.jl:119) / this chunk's final count in the fill pass
@@ -357,125 +475,91 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(const __grid_constant__ W
             if (!__any_sync(FULL, mode == MODE_FAST)) break;
             if (mode != MODE_FAST) continue;
             bool ok = false;
-            if (hB >= 0 && clean) {
-                double ax, ay, w0, w1;
-                ldg256_keep(m.he + hB, pol_keep, ax, ay, w0, w1);
-                int tw1 = __double2loint(w0), tw2 = __double2hiint(w0);
-                float clearf = __int_as_float(__double2loint(w1));
-                double sa = trk.a * ax + trk.b * ay + trk.c;
-                double clearB = fabs((double)clearf);
-                double thr = g * fmax(clearA, clearB);
-                bool clear_ok = (fabs(sa) >= thr) && (fabs(sp) >= thr) && (fabs(sq) >= thr);
-                // the entry edge (v_k, v_k+1) = (u, w) is crossed (sp, sq of opposite sign); the exit is the other edge whose
-                // non-apex end lies on the opposite side of the apex: edge k+1 = (w, apex) or k+2 = (apex, u)
-                bool exit1 = (sa > 0) != (sq > 0);
-                if (clear_ok) {
-                    // general_form(P_i, P_j) of the exit edge in the cell's stored orientation, src/intersection.jl:11-18,57
-                    P2 xi{exit1 ? wx : ax, exit1 ? wy : ay}, xo{exit1 ? ax : ux, exit1 ? ay : uy};
-                    Line L = general_form(xi, xo);
-                    P2 X;
-                    bool par = intersection(trk, L, X);  // same formula as src/intersection.jl:127-138
-                    if (!par) {
-                        P2 Xin{qx, qy};
-                        // int_points are stored in edge-index order; order_intersection_points picks the first
-                        int cellB = hB / 3;
-                        int kin = hB - 3 * cellB;
-                        bool kin_lt_kout = (kin == 0) || (kin == 1 && exit1);
-                        bool in_first = kin_lt_kout ? order_first(right, Xin, X) : !order_first(right, X, Xin);
-                        double l = norm2(qx - X.x, qy - X.y);  // Segment(p, q): norm(p - q), src/segment.jl:32
-                        bool accept = in_first && l > P.lmin;
-                        // cells touching the bounding-box band: the re-location points must not be `inboundary`
-                        if (accept && clearf < 0.0f) accept = bbox_dist(m, qx, qy) > 0.25 * l + 8.0 * P.tiny;
-                        if (accept) {
-                            double pxx = qx, pyy = qy;
-                            int enc = exit1 ? tw1 : tw2;
-                            double si = exit1 ? sq : sa, so = exit1 ? sa : sp;  // s at the exit edge's ordered end points
-                            bool flip = (enc & 1) != 0;
-                            sp = flip ? so : si;
-                            sq = flip ? si : so;
-                            ux = flip ? xo.x : xi.x;
-                            uy = flip ? xo.y : xi.y;
-                            wx = flip ? xi.x : xo.x;
-                            wy = flip ? xi.y : xo.y;
-                            hB = enc < 0 ? -1 : (enc >> 1);
-                            cur = cellB;
-                            qx = X.x;
-                            qy = X.y;
-                            clearA = clearB;
-                            ok = true;
-                            cnt[0]++;
-                            push(cellB, pxx, pyy, X.x, X.y, l);
-                        }
-                    }
+            if (enc >= 0) {
+                const double ax = rax, ay = ray, w0 = rw0, w1 = rw1;
+                const float clearf = __int_as_float(__double2loint(w1));
+                const float clearB = fabsf(clearf);
+                const double sa = ta * ax + tb * ay + tc;
+                const double thr = g * (double)fmaxf(clearA, clearB);
+                // the entry edge is crossed (s1, s2 of opposite sign): the exit edge joins the apex with the end point that
+                // lies on the other side of the track line
+                const bool opp1 = (sa > 0) != (s1 > 0);
+                const bool clear_ok = (fabs(sa) >= thr) && (fabs(s1) >= thr) && (fabs(s2) >= thr);
+                const double kx = opp1 ? e1x : e2x, ky = opp1 ? e1y : e2y, ks = opp1 ? s1 : s2;
+                // exit through edge k+1 = (v_k+1, apex) iff the kept end point is v_k+1, else through k+2 = (apex, v_k).  The
+                // record of the half-edge behind that exit is requested NOW: its latency overlaps the arithmetic below.
+                const bool exit1 = (opp1 == f);
+                const int nenc = exit1 ? __double2loint(w0) : __double2hiint(w0);
+                if (nenc >= 0) ldg256_keep(m.he + (nenc >> 3), pol_keep, rax, ray, rw0, rw1);
+                // general_form of the exit edge (kept end point, apex), src/intersection.jl:11-18,57.  Its orientation is free:
+                // reversing the edge negates (A, B, C) exactly and intersection() is invariant under that negation bit for bit.
+                const double A = ky - ay, B = ax - kx, C = kx * ay - ax * ky;
+                const Recip rn = recip_prepare(sqrt(A * A + B * B + C * C));
+                const double La = div_shared(A, rn), Lb = div_shared(B, rn), Lc = div_shared(C, rn);
+                // intersection(track.ABC, L), src/intersection.jl:127-138 (operands are finite here, so isapprox(a, b) reduces
+                // to |a - b| <= rtol * max(|a|, |b|))
+                const double a = tb * La, b = Lb * ta;
+                const double fa = fabs(a), fb = fabs(b);
+                const bool par = fabs(a - b) <= kRtol * (fa > fb ? fa : fb);
+                const Recip rd = recip_prepare(a - b);
+                const double Xx = div_shared(tc * Lb - Lc * tb, rd), Xy = div_shared(ta * Lc - La * tc, rd);
+                const int kin = (enc >> 1) & 3;
+                // int_points are stored in edge-index order; order_intersection_points (src/intersection.jl:151-159) must put
+                // the entry point first
+                const bool kin_lt_kout = (kin == 0) || (kin == 1 && exit1);
+                const bool in_first = right ? (kin_lt_kout ? (qx < Xx) : !(Xx < qx)) : (kin_lt_kout ? (qx > Xx) : !(Xx > qx));
+                const double dx = qx - Xx, dy = qy - Xy;
+                const double l = sqrt(dx * dx + dy * dy);  // Segment(p, q): norm(p - q), src/segment.jl:32
+                bool accept = clear_ok && !par && in_first && l > P.lmin;
+                // cells touching the bounding-box band: the re-location points must not be `inboundary`
+                if (clearf < 0.0f && accept) accept = bbox_dist(m, qx, qy) > 0.25 * l + 8.0 * P.tiny;
+                // the walker state needed only by the next fast transition is updated unconditionally (the literal path re-arms it)
+                const int cellB = (enc >> 3) / 3;
+                e1x = kx;
+                e1y = ky;
+                s1 = ks;
+                e2x = ax;
+                e2y = ay;
+                s2 = sa;
+                f = (exit1 == ((nenc & 1) != 0));
+                enc = nenc;
+                clearA = clearB;
+                if (accept) {
+                    const double pxx = qx, pyy = qy;
+                    cur = cellB;
+                    qx = Xx;
+                    qy = Xy;
+                    ok = true;
+                    push(cellB, pxx, pyy, Xx, Xy, l);
                 }
             }
-            if (!ok) {
-                // fall back to the literal walk from xp = advance_step(q, tiny, phi), src/track.jl:165-166
-                xpx = qx + sx;
-                xpy = qy + sy;
-                prev = cur;
-                mode = MODE_SLOW;
-            }
+            if (!ok) mode = MODE_SLOW;  // re-locate literally from advance_step(q, tiny, phi), src/track.jl:165-166
         }
         // ------------------------------------------------------------------ LITERAL phase (until one push)
         if (mode == MODE_SLOW) {
-            while (true) {
-                if (++slow_iters > kRunaway) {
-                    status = 3;
-                    endcode = END_ERROR;
-                    mode = MODE_DONE;
-                    break;
+            // advance_step: x + step*Point2D(cos phi, sin phi), src/point.jl:43
+            LitIn in{ta, tb, tc, P.tiny * P.ang.cosp[az], P.tiny * P.ang.sinp[az], qx, qy, cur, right, j == 0 && nseg == 0};
+            LitOut o;
+            literal_until_push(P, in, o);
+            if (P.counters) {
+                atomicAdd(&P.counters[1], (unsigned long long)o.iters);
+                atomicAdd(&P.counters[2], o.nq[0]);
+                if (o.nq[1]) atomicAdd(&P.counters[3], o.nq[1]);
+            }
+            if (o.code == 0) {
+                n_litpush++;
+                push(o.e, o.px, o.py, o.qx, o.qy, o.l);
+                cur = o.e;
+                qx = o.qx;
+                qy = o.qy;
+                if (mode != MODE_DONE && !literal_only && o.e_q >= 0) {
+                    arm(o.e, o.e_q, o.qx, o.qy);
+                    if (clean) mode = MODE_FAST;
                 }
-                cnt[1]++;
-                // find_element's result is discarded on boundary steps (src/track.jl:122-134): test the boundary first
-                if (inboundary(m, xpx, xpy, P.tiny)) {
-                    if (nseg == 0 && j == 0) {
-                        xpx = xpx + sx;
-                        xpy = xpy + sy;
-                        continue;
-                    }
-                    endcode = END_TRACK;
-                    mode = MODE_DONE;
-                    break;
-                }
-                int e = find_element(m, xpx, xpy, 2, &cnt[2]);
-                if (e < 0) {
-                    e = find_element(m, xpx, xpy, P.k, &cnt[2]);
-                    if (e < 0) {
-                        status = 1;  // "Try increasing `k`", src/track.jl:141
-                        endcode = END_ERROR;
-                        mode = MODE_DONE;
-                        break;
-                    }
-                }
-                if (e == prev) {
-                    xpx = xpx + sx;
-                    xpy = xpy + sy;
-                    continue;
-                }
-                P2 p, q;
-                int e_p, e_q;
-                int rc = intersections(m, e, trk, right, p, q, e_p, e_q);
-                if (rc) {
-                    status = rc;
-                    endcode = END_ERROR;
-                    mode = MODE_DONE;
-                    break;
-                }
-                if (isapprox_pt(p, q)) {  // src/track.jl:156-159
-                    xpx = xpx + sx;
-                    xpy = xpy + sy;
-                    continue;
-                }
-                xpx = q.x + sx;
-                xpy = q.y + sy;
-                prev = e;
-                mode = MODE_SLOW;
-                push(e, p.x, p.y, q.x, q.y, norm2(p.x - q.x, p.y - q.y));
-                if (mode == MODE_DONE || literal_only || e_q < 0) break;
-                arm(e, e_q, q.x, q.y);
-                mode = clean ? MODE_FAST : MODE_SLOW;
-                break;
+            } else {
+                endcode = o.code;
+                status = o.status;
+                mode = MODE_DONE;
             }
         }
     }
@@ -486,12 +570,9 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(const __grid_constant__ W
         P.ch.endcode[cidx] = active ? (endcode | (status << 8)) : (END_HANDOFF | (0 << 8));
     }
     if (P.counters) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            unsigned long long v = cnt[q];
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
-            if (lane == 0 && v) atomicAdd(&P.counters[q], v);
-        }
+        unsigned long long v = active ? (unsigned long long)(nseg - n_litpush) : 0ull;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
+        if (lane == 0 && v) atomicAdd(&P.counters[0], v);
     }
 }
 

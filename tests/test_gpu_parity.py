@@ -302,3 +302,16 @@ def test_properties_at_scale():
     rt.segmentize_(tg, check=False)
     s2 = tg.segments
     assert chk == (float(s2["len"].sum()), int(s2["element"].astype(np.int64).sum()))
+
+
+@pytest.mark.parametrize("exp_span", [0, 3, 40, 400, 520, 1022])
+def test_shared_reciprocal_division_is_ieee(pincell_model, exp_span):
+    """geom.cuh div_shared(x, recip_prepare(d)) == x / d bit for bit (2.7e8 quotients per span, incl. hard cases)"""
+    import ctypes as C
+
+    from raytracing_jl_b200 import _lib
+
+    tg = rt.TrackGenerator(pincell_model, 4, 0.8)
+    bad = C.c_int64(-1)
+    _lib.check(tg._ctx, _lib.lib().rt_selftest_division(tg._ctx, 1 << 22, 12345 + exp_span, exp_span, C.byref(bad)))
+    assert bad.value == 0

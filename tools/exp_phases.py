@@ -22,6 +22,7 @@ print("tracks", tg.n_total_tracks, "cells", model.num_cells)
 def run(label, flags=0, reps=3, **opts):
     tg.set_option("chunk_segments", opts.get("chunk_segments", 64))
     tg.set_option("target_walkers", opts.get("target_walkers", 148 * 2048 * 4))
+    tg.set_option("order_grid", opts.get("order_grid", 16))
     best = None
     for _ in range(reps):
         tg.timer_start()
@@ -36,6 +37,11 @@ def run(label, flags=0, reps=3, **opts):
 
 
 run("default")
+if os.environ.get("RT_EXP_QUICK"):
+    for og in (0, 4, 8, 32, 64, 128):
+        run(f"order_grid={og}", order_grid=og)
+    run("no volumes", rt.RT_SEG_NO_VOLUMES)
+    sys.exit(0)
 run("no volumes", rt.RT_SEG_NO_VOLUMES)
 run("no chunks", rt.RT_SEG_NO_CHUNKS)
 run("no chunks, no volumes", rt.RT_SEG_NO_CHUNKS | rt.RT_SEG_NO_VOLUMES)
