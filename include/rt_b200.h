@@ -56,7 +56,8 @@ enum {
     RT_SEG_LITERAL = 1,     /* disable the adjacency fast path: every step re-locates like src/track.jl:122 */
     RT_SEG_NO_VOLUMES = 2,  /* skip the fused fill_volumes accumulation */
     RT_SEG_COUNT_ONLY = 4,  /* count + scan only (no segment buffers are written) */
-    RT_SEG_NO_CHUNKS = 8    /* one walker per track (no sub-track chunks) */
+    RT_SEG_NO_CHUNKS = 8,   /* one walker per track (no sub-track chunks) */
+    RT_SEG_SEQUENTIAL = 16  /* sequential walk kernels only (the two-stage pipeline falls back to them by itself) */
 };
 
 /* ---- context ------------------------------------------------------------------------------------- */
@@ -120,6 +121,7 @@ typedef struct rt_batch {
     const double *d_px, *d_py, *d_qx, *d_qy, *d_len; /* DEVICE SoA */
     const int32_t *d_element;     /* DEVICE, 1-based element ids */
     void *stream;                 /* cudaStream_t the batch was produced on */
+    int32_t attempt;              /* 1: the call restarted sequentially after a failed verification; drop attempt-0 batches */
 } rt_batch;
 typedef int (*rt_batch_cb)(const rt_batch *batch, void *user);
 
@@ -151,6 +153,8 @@ int rt_comm_init(rt_ctx *ctx, int32_t n_ranks, int32_t rank, const char id[128])
  * stats[0..7] of the last rt_segmentize: kernel launches, fast transitions, slow (literal) iterations,
  * nearest-node queries, knn queries, count-pass ms, fill-pass ms, scan+volumes ms. */
 int rt_stats(rt_ctx *ctx, double stats[8]);
+/* named scalars of the last rt_segmentize: "verify_fallbacks", "eval_ms" (k_eval alone), "n_units", "segment_capacity" */
+int rt_info(rt_ctx *ctx, const char *key, double *value);
 /* CUDA-event time (ms) of the last call's device work, by phase: 0 upload+prep, 1 trace, 2 count,
  * 3 scan, 4 fill, 5 volumes(+allreduce) */
 int rt_phase_ms(rt_ctx *ctx, double ms[6]);
@@ -161,7 +165,9 @@ int rt_selftest_division(rt_ctx *ctx, int64_t n_threads, uint64_t seed, int32_t 
 
 /* tuning knobs: "chunk_segments" (minimum expected segments per sub-track chunk, default 64),
  * "target_walkers" (chunks are sized so that about this many walkers exist, default 148*2048*4),
- * "order_grid" (G: walkers are launched in Morton order of a G x G tiling of the domain, default 16, 0 = uid order) */
+ * "order_grid" (G: walkers are launched in Morton order of a G x G tiling of the domain, default 16, 0 = uid order),
+ * "pipeline" (0: sign-test count walk + geometric fill walk [default], 1: sequential walks only, 2: sign-test walks + one
+ * thread per segment; 0 and 2 verify themselves and restart in mode 1 on any disagreement) */
 int rt_set_option(rt_ctx *ctx, const char *name, double value);
 /* CUDA-event stopwatch on the context's launching stream (bench harness: torch.cuda.Event cannot see it). */
 int rt_timer_start(rt_ctx *ctx);

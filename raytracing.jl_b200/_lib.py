@@ -15,7 +15,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SO_PATH = os.environ.get("RT_B200_LIB") or os.path.join(_PKG, "librt_b200.so")  # RT_B200_LIB: an alternative build
 _CSRC = os.path.join(_PKG, "csrc")
-_SOURCES = ["rt_b200.cu", "geom.cuh", "mesh_dev.cuh", "walk.cuh", "trace.cuh", "scan.cuh"]
+_SOURCES = ["rt_b200.cu", "geom.cuh", "mesh_dev.cuh", "walk.cuh", "topo.cuh", "trace.cuh", "scan.cuh"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -52,7 +52,7 @@ _vp = C.c_void_p
 class rt_batch(C.Structure):
     _fields_ = [("uid_begin", C.c_int64), ("uid_end", C.c_int64), ("n_segments", C.c_int64), ("d_offsets", _vp),
                 ("offset_base", C.c_int64), ("d_px", _vp), ("d_py", _vp), ("d_qx", _vp), ("d_qy", _vp), ("d_len", _vp),
-                ("d_element", _vp), ("stream", _vp)]
+                ("d_element", _vp), ("stream", _vp), ("attempt", C.c_int32)]
 
 
 BATCH_CB = C.CFUNCTYPE(C.c_int, C.POINTER(rt_batch), _vp)
@@ -81,13 +81,14 @@ SYMBOLS = {
     "rt_comm_init": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_char_p]),
     "rt_stats": (C.c_int, [_vp, _f64]),
     "rt_phase_ms": (C.c_int, [_vp, _f64]),
+    "rt_info": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_double)]),
     "rt_set_option": (C.c_int, [_vp, C.c_char_p, C.c_double]),
     "rt_selftest_division": (C.c_int, [_vp, C.c_int64, C.c_uint64, C.c_int32, C.POINTER(C.c_int64)]),
     "rt_timer_start": (C.c_int, [_vp]),
     "rt_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_double)]),
 }
 
-RT_SEG_LITERAL, RT_SEG_NO_VOLUMES, RT_SEG_COUNT_ONLY, RT_SEG_NO_CHUNKS = 1, 2, 4, 8
+RT_SEG_LITERAL, RT_SEG_NO_VOLUMES, RT_SEG_COUNT_ONLY, RT_SEG_NO_CHUNKS, RT_SEG_SEQUENTIAL = 1, 2, 4, 8, 16
 
 _lib = None
 

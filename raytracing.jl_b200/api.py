@@ -392,6 +392,11 @@ class TrackGenerator(TrackLayout):
         return dict(zip(["launches", "fast_transitions", "literal_iterations", "nn_queries", "knn_queries", "count_ms",
                          "fill_ms", "scan_ms"], s.tolist()))
 
+    def info(self, key: str) -> float:
+        v = C.c_double(0.0)
+        _lib.check(self._ctx, _lib.lib().rt_info(self._ctx, key.encode(), C.byref(v)))
+        return v.value
+
     def neighbours(self):
         nb = np.zeros(3 * self.mesh.num_cells, np.int32)
         _lib.check(self._ctx, _lib.lib().rt_mesh_neighbours(self._ctx, nb))

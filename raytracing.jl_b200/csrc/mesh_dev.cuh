@@ -29,7 +29,7 @@ struct __align__(32) HalfEdge {
     int tw1, tw2;   // entry half-edge of the neighbour across edge k+1 = (v_k+1, apex) / k+2 = (apex, v_k),
                     // encoded (3*cell' + k') << 3 | k' << 1 | flip (flip: end points in opposite order); -1 on the boundary
     float clear;    // = CellRec::clear of this cell
-    int pad0;
+    float clear2;   // l_min / sigma: a lone vertex at least this far from the track line has a chord longer than l_min
 };
 static_assert(sizeof(HalfEdge) == 32, "HalfEdge must be 32 bytes");
 
@@ -180,7 +180,7 @@ __global__ void k_node_reach(DevMesh m, const CellRec *cells, const MeshScalars 
 }
 
 __global__ void k_finalize_clear(DevMesh m, CellRec *cells, HalfEdge *he, const float *qual, const float *bdist,
-                                 const MeshScalars *sc, const float *node_reach, double tiny) {
+                                 const MeshScalars *sc, const float *node_reach, double tiny, double lmin) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= m.n_cells) return;
     const CellRec &r = cells[c];
@@ -196,7 +196,15 @@ __global__ void k_finalize_clear(DevMesh m, CellRec *cells, HalfEdge *he, const 
     else if (boundary)
         cf = -cf;
     cells[c].clear = cf;
-    for (int k = 0; k < 3; ++k) he[3 * c + k].clear = cf;
+    // chord >= d * sin(gamma) >= d * sigma for a lone vertex at distance d from the track line (topo.cuh)
+    double c2 = lmin * 1.001 * (double)qual[c];
+    float c2f = (float)c2;
+    if (!(c2f >= c2)) c2f = nextafterf(c2f, INFINITY);
+    if (!isfinite(c2)) c2f = INFINITY;
+    for (int k = 0; k < 3; ++k) {
+        he[3 * c + k].clear = cf;
+        he[3 * c + k].clear2 = c2f;
+    }
 }
 
 // twin[3c+k]: where a track that leaves cell c through edge k = (v_k, v_k+1) enters the neighbour
@@ -230,7 +238,7 @@ __global__ void k_half_edges(DevMesh m, const CellRec *cells, const int *twin, H
     h.tw1 = twin[3 * c + k1];
     h.tw2 = twin[3 * c + k2];
     h.clear = INFINITY;
-    h.pad0 = 0;
+    h.clear2 = INFINITY;
     he[t] = h;
 }
 

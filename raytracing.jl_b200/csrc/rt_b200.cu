@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "scan.cuh"
+#include "topo.cuh"
 #include "trace.cuh"
 
 using namespace rt;
@@ -73,6 +74,14 @@ struct rt_ctx {
     DevBuf b_count, b_status, b_offsets, b_tile, b_vol, b_voln, b_counters, b_bad;
     DevBuf b_nch, b_blk_chunks, b_unit_base, b_unit_block, b_ch_i, b_ch_d;  // chunk plan (walk.cuh ChunkPlan)
     DevBuf b_order, b_okeys, b_ohist;  // spatial execution order of the units
+    DevBuf b_evalblk;
+    DevBuf b_rec, b_verify, b_tsum;    // two-stage pipeline: per-segment records, verification flag, per-track length sums
+    int opt_pipeline = 0;              // 0: hybrid (sign-test count walk + geometric fill walk), 1: sequential (walk.cuh only),
+                                       // 2: two-stage (sign-test walks + one thread per segment); 0 and 2 fall back to 1
+    int verify_fallbacks = 0;
+    int opt_debug_verify_fail = 0;     // test hook: make the verification of the two-stage pipeline fail
+    double eval_ms = 0.0;
+    cudaEvent_t ev2[2] = {nullptr, nullptr};
     int opt_order_grid = 16;           // G x G tiles (0: identity order)
     long long n_units = 0;
     double opt_chunk_segments = 64.0;               // minimum expected segments per chunk
@@ -157,7 +166,8 @@ extern "C" int rt_create(rt_ctx **out, int device) {
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev[0]) != cudaSuccess || cudaEventCreate(&ctx->ev[1]) != cudaSuccess ||
-        cudaEventCreate(&ctx->tev[0]) != cudaSuccess || cudaEventCreate(&ctx->tev[1]) != cudaSuccess) {
+        cudaEventCreate(&ctx->tev[0]) != cudaSuccess || cudaEventCreate(&ctx->tev[1]) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev2[0]) != cudaSuccess || cudaEventCreate(&ctx->ev2[1]) != cudaSuccess) {
         delete ctx;
         return RT_ERR_CUDA;
     }
@@ -176,7 +186,7 @@ extern "C" void rt_destroy(rt_ctx *ctx) {
                      &ctx->b_voln,    &ctx->b_counters,   &ctx->b_bad,      &ctx->b_seg_d,   &ctx->b_seg_e,
                      &ctx->b_twin,    &ctx->b_he,         &ctx->b_node_reach,
                      &ctx->b_nch,     &ctx->b_blk_chunks, &ctx->b_unit_base, &ctx->b_unit_block, &ctx->b_ch_i, &ctx->b_ch_d,
-                     &ctx->b_order,   &ctx->b_okeys,      &ctx->b_ohist};
+                     &ctx->b_order,   &ctx->b_okeys,      &ctx->b_ohist,     &ctx->b_rec,     &ctx->b_verify,    &ctx->b_tsum,      &ctx->b_evalblk};
     for (DevBuf *b : all) release(*b);
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
     if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
@@ -612,47 +622,37 @@ static int ensure_segment_buffers(rt_ctx *ctx, long long want) {
     return RT_OK;
 }
 
-extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rtol, int32_t max_iter, const double *delta_eff,
-                             uint32_t flags, rt_batch_cb cb, void *cb_user, int64_t *n_segments_total, int64_t *first_bad_uid,
-                             int32_t *bad_status) {
-    if (!ctx) return RT_ERR_ARG;
-    if (!ctx->traced)
-        return fail(ctx, RT_ERR_NOT_TRACED, "Segmentation is intended after tracing. Please, call `trace!` first!");
-    if (k < 1 || max_iter < 0) return fail(ctx, RT_ERR_ARG, "rt_segmentize: bad k / max_iter");
-    const bool want_vol = !(flags & RT_SEG_NO_VOLUMES);
-    if (want_vol && !delta_eff) return fail(ctx, RT_ERR_ARG, "rt_segmentize: delta_eff is required unless RT_SEG_NO_VOLUMES");
-    CK(cudaSetDevice(ctx->device));
+// fast transitions only accept chords that are certainly not dropped by isapprox(p, q) (src/track.jl:156) and long enough for
+// the re-location argument: l > l_min = max(8*tiny, rtol * largest possible |point|)
+static double lmin_of(const DevMesh &m, double tiny_step) {
+    double nb = hypot(fmax(fabs(m.bbmin[0]), fabs(m.bbmax[0])), fmax(fabs(m.bbmin[1]), fabs(m.bbmax[1])));
+    return fmax(8.0 * tiny_step, kRtol * nb * (1.0 + 1e-6) + 1e-300);
+}
+
+// One complete count -> scan -> fill execution.
+//   mode 1 (sequential): k_walk<false> counts, k_walk<true> fills (walk.cuh);
+//   mode 0 (hybrid):     k_topo<false> counts by sign tests (topo.cuh), k_walk<true> fills and re-derives the same decisions
+//                        from the exact geometry;
+//   mode 2 (two-stage):  k_topo<false> counts, k_topo<true> writes per-segment records, k_eval evaluates one segment per thread.
+// In modes 0 and 2 the length check (src/track.jl:171-175) runs after the fill (k_track_status).  *verify_failed reports that
+// the fill disagreed with the count (mode 0) or that a segment broke a geometric fast-path condition (mode 2): the caller then
+// repeats the call in mode 1.
+static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol, int32_t max_iter, uint32_t flags, rt_batch_cb cb,
+                           void *cb_user, int mode, int attempt, bool *verify_failed, unsigned long long *bad_out) {
+    const bool topo = mode == 2, topo_count = mode != 1;
     cudaStream_t st = ctx->stream;
     const long long n = ctx->n_shard;
     const int n2 = ctx->n2;
     DevMesh &m = ctx->m;
-    ctx->segmented = false;
-    ctx->vol_valid = false;
-
-    if (ctx->clear_tiny != tiny_step) {
-        k_finalize_clear<<<blocks_for(m.n_cells, 128), 128, 0, st>>>(m, (CellRec *)ctx->b_cells.p, (HalfEdge *)ctx->b_he.p,
-                                                                     (const float *)ctx->b_qual.p, (const float *)ctx->b_bdist.p,
-                                                                     (const MeshScalars *)ctx->b_sc.p,
-                                                                     (const float *)ctx->b_node_reach.p, tiny_step);
-        CK(cudaGetLastError());
-        ctx->clear_tiny = tiny_step;
-    }
-    if (want_vol) {
-        CK(cudaMemcpyAsync((double *)ctx->b_ang_d.p + 6 * (size_t)n2, delta_eff, sizeof(double) * n2, cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));
-        ctx->has_delta = true;
-        CK(ensure(ctx->b_vol, sizeof(double) * (size_t)m.n_cells));
-        CK(cudaMemsetAsync(ctx->b_vol.p, 0, sizeof(double) * (size_t)m.n_cells, st));
-    }
+    const bool want_vol = !(flags & RT_SEG_NO_VOLUMES);
+    *verify_failed = false;
+    *bad_out = ~0ULL;
+    if (want_vol) CK(cudaMemsetAsync(ctx->b_vol.p, 0, sizeof(double) * (size_t)m.n_cells, st));
     size_t nn = (size_t)std::max<long long>(n, 1);
-    CK(ensure(ctx->b_count, sizeof(int) * nn));
-    CK(ensure(ctx->b_status, sizeof(int) * nn));
-    CK(ensure(ctx->b_offsets, sizeof(long long) * (nn + 1)));
-    CK(ensure(ctx->b_counters, sizeof(unsigned long long) * 4));
-    CK(ensure(ctx->b_bad, sizeof(unsigned long long)));
     CK(cudaMemsetAsync(ctx->b_counters.p, 0, sizeof(unsigned long long) * 4, st));
     CK(cudaMemsetAsync(ctx->b_bad.p, 0xff, sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(ctx->b_offsets.p, 0, sizeof(long long) * (nn + 1), st));
+    CK(cudaMemsetAsync(ctx->b_verify.p, 0, sizeof(int), st));
 
     WalkParams P{};
     P.m = m;
@@ -663,22 +663,22 @@ extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rt
     P.ang.cosp = ad + 2 * n2;
     P.ang.delta_eff = ad + 6 * n2;
     P.tiny = tiny_step;
-    P.rtol = rtol;
+    P.rtol = topo_count ? -1.0 : rtol;  // sign-test count: the length check runs after the fill (k_track_status)
     P.k = k;
     P.max_iter = max_iter;
     P.flags = flags;
-    // fast path only accepts chords that are certainly not dropped by isapprox(p, q) (src/track.jl:156) and long
-    // enough for the re-location argument: l > max(8*tiny, rtol * largest possible |point|)
-    double nb = hypot(fmax(fabs(m.bbmin[0]), fabs(m.bbmax[0])), fmax(fabs(m.bbmin[1]), fabs(m.bbmax[1])));
-    P.lmin = fmax(8.0 * tiny_step, kRtol * nb * (1.0 + 1e-6) + 1e-300);
+    P.lmin = lmin_of(m, tiny_step);
+    P.lmax = ctx->lmax;
+    P.smax = ctx->smax;
     P.count = (int *)ctx->b_count.p;
     P.status = (int *)ctx->b_status.p;
     P.offsets = (const long long *)ctx->b_offsets.p;
     P.counters = (unsigned long long *)ctx->b_counters.p;
+    P.verify_fail = (int *)ctx->b_verify.p;
     const bool count_only = (flags & RT_SEG_COUNT_ONLY) != 0;
     double launches = 0;
 
-    // ---- chunk plan: cut tracks so that ~target_walkers independent walkers exist, >= 64 segments each
+    // ---- chunk plan: cut tracks so that ~target_walkers independent walkers exist, >= chunk_segments segments each
     tic(ctx);
     P.n_tracks = n;
     P.trk_begin = 0;
@@ -745,8 +745,12 @@ extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rt
         // ---- seeds, count pass, per-track fix-up
         P.vol = nullptr;
         k_seed<<<blocks_for(n_units * 32, 128), 128, 0, st>>>(P);
-        P.vol = (want_vol && count_only) ? (double *)ctx->b_vol.p : nullptr;
-        k_walk<false><<<blocks_for(n_units * 32, 128), 128, 0, st>>>(P);
+        if (topo_count) {
+            k_topo<false><<<blocks_for(n_units * 32, kTopoThreads), kTopoThreads, 0, st>>>(P);
+        } else {
+            P.vol = (want_vol && count_only) ? (double *)ctx->b_vol.p : nullptr;
+            k_walk<false><<<blocks_for(n_units * 32, kWalkThreads), kWalkThreads, 0, st>>>(P);
+        }
         k_fixup_tracks<<<blocks_for(n, 128), 128, 0, st>>>(P);
         launches += 3;
     }
@@ -755,23 +759,18 @@ extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rt
     // ---- scan
     tic(ctx);
     long long total = 0;
-    unsigned long long bad = ~0ULL;
     if (n > 0) {
         CK((exclusive_scan<int, long long>(ctx, (const int *)ctx->b_count.p, (long long *)ctx->b_offsets.p, n)));
-        k_first_bad<<<blocks_for(n, 256), 256, 0, st>>>((const int *)ctx->b_status.p, n, (unsigned long long *)ctx->b_bad.p);
-        launches += 4;
+        launches += 3;
         CK(cudaMemcpyAsync(&total, (long long *)ctx->b_offsets.p + n, sizeof(long long), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&bad, ctx->b_bad.p, sizeof(bad), cudaMemcpyDeviceToHost, st));
     }
     ctx->phase_ms[3] = toc(ctx);
     CK(cudaStreamSynchronize(st));
     ctx->total_segments = total;
-    if (n_segments_total) *n_segments_total = total;
-    if (first_bad_uid) *first_bad_uid = 0;
-    if (bad_status) *bad_status = 0;
 
     // ---- fill pass (possibly in uid batches over a recycled buffer)
     ctx->phase_ms[4] = 0.0;
+    ctx->eval_ms = 0.0;
     ctx->res_trk_begin = ctx->res_trk_end = 0;
     ctx->res_off_base = 0;
     ctx->res_nseg = 0;
@@ -779,19 +778,47 @@ extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rt
         long long cap = total;
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
-        long long fit = (long long)((double)(free_b + ctx->b_seg_d.bytes + ctx->b_seg_e.bytes) * 0.92 / 44.0);
+        const double bytes_per_seg = topo ? 48.0 : 44.0;
+        long long fit = (long long)((double)(free_b + ctx->b_seg_d.bytes + ctx->b_seg_e.bytes + ctx->b_rec.bytes) * 0.92 / bytes_per_seg);
         if (ctx->cap_cfg > 0) cap = std::min(cap, (long long)ctx->cap_cfg);
         cap = std::min(cap, fit);
         int rc = ensure_segment_buffers(ctx, cap);
         if (rc) return rc;
+        if (topo) CK(ensure(ctx->b_rec, sizeof(int) * (size_t)ctx->cap));
+        if (topo_count) {
+            CK(ensure(ctx->b_tsum, sizeof(double) * nn));
+            CK(cudaMemsetAsync(ctx->b_tsum.p, 0, sizeof(double) * nn, st));
+        }
         P.opx = ctx->s_px;
         P.opy = ctx->s_py;
         P.oqx = ctx->s_qx;
         P.oqy = ctx->s_qy;
         P.olen = ctx->s_len;
         P.oelem = ctx->s_elem;
+        P.rec = (int *)ctx->b_rec.p;
+        P.tsum = topo_count ? (double *)ctx->b_tsum.p : nullptr;
         P.vol = want_vol ? (double *)ctx->b_vol.p : nullptr;
         P.counters = nullptr;
+        EvalParams E{};
+        E.m = m;
+        E.t = ctx->t;
+        E.ang = P.ang;
+        E.offsets = P.offsets;
+        E.n_tracks = n;
+        E.rec = P.rec;
+        E.opx = P.opx;
+        E.opy = P.opy;
+        E.oqx = P.oqx;
+        E.oqy = P.oqy;
+        E.olen = P.olen;
+        E.oelem = P.oelem;
+        E.vol = P.vol;
+        E.lmin = ctx->opt_debug_verify_fail ? INFINITY : P.lmin;
+        if (ctx->opt_debug_verify_fail && !topo && topo_count) CK(cudaMemsetAsync(ctx->b_verify.p, 1, 1, st));
+        E.verify_fail = P.verify_fail;
+        E.status = P.status;
+        E.tsum = P.tsum;
+        E.rtol = rtol;
         std::vector<long long> h_off;
         if (total > cap) {
             h_off.resize((size_t)n + 1);
@@ -817,31 +844,139 @@ extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rt
                 P.unit_begin = h_unit_base[(size_t)(b >> 5)];
                 P.unit_end = h_unit_base[(size_t)((e - 1) >> 5) + 1];
             }
-            k_walk<true><<<blocks_for((P.unit_end - P.unit_begin) * 32, 128), 128, 0, st>>>(P);
-            launches += 1;
+            const long long nseg_b = (total > cap ? h_off[e] : total) - P.offset_base;
+            if (topo) {
+                k_topo<true><<<blocks_for((P.unit_end - P.unit_begin) * 32, kTopoThreads), kTopoThreads, 0, st>>>(P);
+                E.trk_begin = b;
+                E.trk_end = e;
+                E.offset_base = P.offset_base;
+                E.n_seg = nseg_b;
+                CK(cudaEventRecord(ctx->ev2[0], st));
+                if (nseg_b > 0) {
+                    const long long n_eb = (nseg_b + kEvalPerBlock - 1) / kEvalPerBlock;
+                    CK(ensure(ctx->b_evalblk, sizeof(long long) * (size_t)n_eb));
+                    k_eval_blocks<<<blocks_for(n_eb, 256), 256, 0, st>>>(E, n_eb, (long long *)ctx->b_evalblk.p);
+                    k_eval<<<(unsigned)n_eb, kEvalThreads, 0, st>>>(E, (const long long *)ctx->b_evalblk.p);
+                }
+                CK(cudaEventRecord(ctx->ev2[1], st));
+                k_track_status<<<blocks_for(e - b, 128), 128, 0, st>>>(E);
+                launches += 4;
+            } else {
+                k_walk<true><<<blocks_for((P.unit_end - P.unit_begin) * 32, kWalkThreads), kWalkThreads, 0, st>>>(P);
+                launches += 1;
+                if (topo_count) {
+                    E.trk_begin = b;
+                    E.trk_end = e;
+                    E.offset_base = P.offset_base;
+                    E.n_seg = nseg_b;
+                    k_track_status<<<blocks_for(e - b, 128), 128, 0, st>>>(E);
+                    launches += 1;
+                }
+            }
             CK(cudaGetLastError());
             ctx->res_trk_begin = b;
             ctx->res_trk_end = e;
             ctx->res_off_base = P.offset_base;
-            ctx->res_nseg = (total > cap ? h_off[e] : total) - P.offset_base;
+            ctx->res_nseg = nseg_b;
+            if (topo_count) {
+                int vf = 0;
+                CK(cudaMemcpyAsync(&vf, ctx->b_verify.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                if (topo) {
+                    float ems = 0.f;
+                    cudaEventElapsedTime(&ems, ctx->ev2[0], ctx->ev2[1]);
+                    ctx->eval_ms += ems;
+                }
+                if (vf) {
+                    *verify_failed = true;
+                    ctx->phase_ms[4] = toc(ctx);
+                    return RT_OK;
+                }
+            }
             if (cb) {
                 rt_batch bt;
                 int rcb = rt_segments_device(ctx, &bt);
                 if (rcb) return rcb;
+                bt.attempt = attempt;
                 if (cb(&bt, cb_user)) return fail(ctx, RT_ERR_ARG, "rt_segmentize: batch callback asked to stop");
             }
             b = e;
         }
         ctx->phase_ms[4] = toc(ctx);
     }
+    unsigned long long bad = ~0ULL;
+    if (n > 0) {
+        k_first_bad<<<blocks_for(n, 256), 256, 0, st>>>((const int *)ctx->b_status.p, n, (unsigned long long *)ctx->b_bad.p);
+        launches += 1;
+        CK(cudaMemcpyAsync(&bad, ctx->b_bad.p, sizeof(bad), cudaMemcpyDeviceToHost, st));
+    }
     unsigned long long hc[4] = {0, 0, 0, 0};
     CK(cudaMemcpyAsync(hc, ctx->b_counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    ctx->stats[0] = launches;
+    ctx->stats[0] += launches;
     for (int q = 0; q < 4; ++q) ctx->stats[1 + q] = (double)hc[q];
     ctx->stats[5] = ctx->phase_ms[2];
     ctx->stats[6] = ctx->phase_ms[4];
     ctx->stats[7] = ctx->phase_ms[3];
+    *bad_out = bad;
+    return RT_OK;
+}
+
+extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rtol, int32_t max_iter, const double *delta_eff,
+                             uint32_t flags, rt_batch_cb cb, void *cb_user, int64_t *n_segments_total, int64_t *first_bad_uid,
+                             int32_t *bad_status) {
+    if (!ctx) return RT_ERR_ARG;
+    if (!ctx->traced)
+        return fail(ctx, RT_ERR_NOT_TRACED, "Segmentation is intended after tracing. Please, call `trace!` first!");
+    if (k < 1 || max_iter < 0) return fail(ctx, RT_ERR_ARG, "rt_segmentize: bad k / max_iter");
+    const bool want_vol = !(flags & RT_SEG_NO_VOLUMES);
+    if (want_vol && !delta_eff) return fail(ctx, RT_ERR_ARG, "rt_segmentize: delta_eff is required unless RT_SEG_NO_VOLUMES");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const long long n = ctx->n_shard;
+    const int n2 = ctx->n2;
+    DevMesh &m = ctx->m;
+    ctx->segmented = false;
+    ctx->vol_valid = false;
+
+    if (ctx->clear_tiny != tiny_step) {
+        k_finalize_clear<<<blocks_for(m.n_cells, 128), 128, 0, st>>>(m, (CellRec *)ctx->b_cells.p, (HalfEdge *)ctx->b_he.p,
+                                                                     (const float *)ctx->b_qual.p, (const float *)ctx->b_bdist.p,
+                                                                     (const MeshScalars *)ctx->b_sc.p,
+                                                                     (const float *)ctx->b_node_reach.p, tiny_step, lmin_of(m, tiny_step));
+        CK(cudaGetLastError());
+        ctx->clear_tiny = tiny_step;
+    }
+    if (want_vol) {
+        CK(cudaMemcpyAsync((double *)ctx->b_ang_d.p + 6 * (size_t)n2, delta_eff, sizeof(double) * n2, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->has_delta = true;
+        CK(ensure(ctx->b_vol, sizeof(double) * (size_t)m.n_cells));
+    }
+    size_t nn = (size_t)std::max<long long>(n, 1);
+    CK(ensure(ctx->b_count, sizeof(int) * nn));
+    CK(ensure(ctx->b_status, sizeof(int) * nn));
+    CK(ensure(ctx->b_offsets, sizeof(long long) * (nn + 1)));
+    CK(ensure(ctx->b_counters, sizeof(unsigned long long) * 4));
+    CK(ensure(ctx->b_bad, sizeof(unsigned long long)));
+    CK(ensure(ctx->b_verify, sizeof(int)));
+
+    // the two-stage pipeline unless a flag asks for behaviour only the sequential kernels have
+    int mode = (flags & (RT_SEG_SEQUENTIAL | RT_SEG_COUNT_ONLY)) ? 1 : ctx->opt_pipeline;
+    ctx->stats[0] = 0;
+    ctx->verify_fallbacks = 0;
+    unsigned long long bad = ~0ULL;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        bool vf = false;
+        int rc = segmentize_once(ctx, tiny_step, k, rtol, max_iter, flags, cb, cb_user, mode, attempt, &vf, &bad);
+        if (rc) return rc;
+        if (!vf) break;
+        mode = 1;  // count and fill disagreed / a geometric fast-path condition failed: redo everything sequentially
+        ctx->verify_fallbacks += 1;
+    }
+    if (n_segments_total) *n_segments_total = ctx->total_segments;
+    if (first_bad_uid) *first_bad_uid = 0;
+    if (bad_status) *bad_status = 0;
     ctx->segmented = true;
     ctx->vol_valid = want_vol;
     if (bad != ~0ULL) {
@@ -897,6 +1032,7 @@ extern "C" int rt_segments_device(rt_ctx *ctx, rt_batch *view) {
     view->d_len = ctx->s_len;
     view->d_element = ctx->s_elem;
     view->stream = (void *)ctx->stream;
+    view->attempt = 0;
     return RT_OK;
 }
 
@@ -1029,6 +1165,22 @@ extern "C" int rt_stats(rt_ctx *ctx, double stats[8]) {
     return RT_OK;
 }
 
+extern "C" int rt_info(rt_ctx *ctx, const char *key, double *value) {
+    if (!ctx || !key || !value) return RT_ERR_ARG;
+    std::string k(key);
+    if (k == "verify_fallbacks")
+        *value = ctx->verify_fallbacks;
+    else if (k == "eval_ms")
+        *value = ctx->eval_ms;
+    else if (k == "n_units")
+        *value = (double)ctx->n_units;
+    else if (k == "segment_capacity")
+        *value = (double)ctx->cap;
+    else
+        return fail(ctx, RT_ERR_ARG, "rt_info: unknown key %s", key);
+    return RT_OK;
+}
+
 extern "C" int rt_phase_ms(rt_ctx *ctx, double ms[6]) {
     if (!ctx || !ms) return RT_ERR_ARG;
     memcpy(ms, ctx->phase_ms, sizeof(ctx->phase_ms));
@@ -1062,6 +1214,10 @@ extern "C" int rt_set_option(rt_ctx *ctx, const char *name, double value) {
         ctx->opt_target_walkers = value;
     else if (n == "order_grid" && value >= 0.0 && value <= 256.0)
         ctx->opt_order_grid = (int)value;
+    else if (n == "pipeline" && (value == 0.0 || value == 1.0 || value == 2.0))
+        ctx->opt_pipeline = (int)value;
+    else if (n == "debug_verify_fail")
+        ctx->opt_debug_verify_fail = value != 0.0;
     else
         return fail(ctx, RT_ERR_ARG, "rt_set_option: unknown option or bad value: %s", name);
     return RT_OK;

@@ -59,6 +59,7 @@ struct WalkParams {
     AngleTabs ang;
     ChunkPlan ch;
     double tiny, rtol, lmin;
+    double lmax, smax;  // longest mesh edge, largest |coordinate| (error bounds of the two-stage pipeline)
     int k, max_iter;
     unsigned flags;
     int *count;   // per track (fix-up output)
@@ -69,6 +70,9 @@ struct WalkParams {
     int *oelem;
     double *vol;                   // unnormalised sum(delta_eff*len) per element, or nullptr
     unsigned long long *counters;  // [fast transitions, literal iterations, nn queries, knn queries] or nullptr
+    int *rec;                      // two-stage pipeline (topo.cuh): per-segment records
+    int *verify_fail;
+    double *tsum;                  // two-stage pipeline: per-track sum of segment lengths
 };
 
 enum { MODE_FAST = 0, MODE_SLOW = 1, MODE_DONE = 2 };
@@ -569,6 +573,10 @@ __global__ void __launch_bounds__(kWalkThreads, RT_WALK_MIN_BLOCKS) k_walk(const
         P.ch.sum[cidx] = sum;
         P.ch.endcode[cidx] = active ? (endcode | (status << 8)) : (END_HANDOFF | (0 << 8));
     }
+    if (FILL && active && P.tsum) {  // hybrid pipeline: the counts came from the sign-test walk (topo.cuh)
+        atomicAdd(&P.tsum[t], sum);
+        if (nseg != limit) atomicExch(P.verify_fail, 1);  // this walk ended before producing the counted segments
+    }
     if (P.counters) {
         unsigned long long v = active ? (unsigned long long)(nseg - n_litpush) : 0ull;
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
@@ -613,7 +621,8 @@ __global__ void k_fixup_tracks(const __grid_constant__ WalkParams P) {
         P.ch.count[cidx] = cnt;
         total += cnt;
     }
-    if (status == 0 && (truncated || !isapprox(P.t.len[t], sum, 0.0, P.rtol))) status = 2;
+    // P.rtol < 0: the two-stage pipeline checks the length after the evaluation (k_track_check)
+    if (P.rtol >= 0.0 && status == 0 && (truncated || !isapprox(P.t.len[t], sum, 0.0, P.rtol))) status = 2;
     P.count[t] = total;
     P.status[t] = status;
 }

@@ -56,7 +56,7 @@ def test_library_does_not_depend_on_the_oracle(so):
 def test_status_codes_match_header():
     src = open(os.path.join(ROOT, "include", "rt_b200.h")).read()
     assert re.search(r"RT_ERR_TRACK\s*=\s*-8", src) and re.search(r"RT_ERR_NO_EXIT\s*=\s*-4", src)
-    for name, val in (("RT_SEG_LITERAL", 1), ("RT_SEG_NO_VOLUMES", 2), ("RT_SEG_COUNT_ONLY", 4), ("RT_SEG_NO_CHUNKS", 8)):
+    for name, val in (("RT_SEG_LITERAL", 1), ("RT_SEG_NO_VOLUMES", 2), ("RT_SEG_COUNT_ONLY", 4), ("RT_SEG_NO_CHUNKS", 8), ("RT_SEG_SEQUENTIAL", 16)):
         assert re.search(rf"{name}\s*=\s*{val}\b", src) and getattr(_lib, name) == val
     assert [int(rt.Vacuum), int(rt.Reflective), int(rt.Periodic)] == [0, 1, 2]  # src/boundary.jl:12-16
     assert [int(rt.Forward), int(rt.Backward)] == [0, 1]  # src/track.jl:11-14

@@ -27,7 +27,7 @@ def bcs_of(codes):
     return rt.BoundaryConditions(top=t, bottom=b, right=r, left=l)
 
 
-def run_both(model, n_azim, delta, bcs=(0, 0, 0, 0), flags=0, k=5, capacity=0, chunk_segments=None):
+def run_both(model, n_azim, delta, bcs=(0, 0, 0, 0), flags=0, k=5, capacity=0, chunk_segments=None, pipeline=None):
     mesh = rt.Mesh(model)
     otg = OracleTrackGenerator(OracleMesh.from_mesh(mesh), n_azim, delta, bcs=bcs)
     otg.trace()
@@ -37,6 +37,8 @@ def run_both(model, n_azim, delta, bcs=(0, 0, 0, 0), flags=0, k=5, capacity=0, c
     if chunk_segments:
         tg.set_option("chunk_segments", chunk_segments)
         tg.set_option("target_walkers", 1e9)
+    if pipeline is not None:
+        tg.set_option("pipeline", pipeline)
     if capacity:
         from raytracing_jl_b200 import _lib
         _lib.lib().rt_set_segment_capacity(tg._ctx, capacity)
@@ -111,8 +113,13 @@ def test_trace_matches_oracle_bitwise(pincell_model, n_azim, delta, bcs):
 
 
 # ---- segmentize! -------------------------------------------------------------------------------------
+SEQ = rt.RT_SEG_SEQUENTIAL
+
+
 @pytest.mark.parametrize("flags,chunk", [(0, None), (rt.RT_SEG_LITERAL, None), (rt.RT_SEG_NO_CHUNKS, None),
-                                         (rt.RT_SEG_LITERAL | rt.RT_SEG_NO_CHUNKS, None), (0, 4), (0, 1), (rt.RT_SEG_LITERAL, 3)])
+                                         (rt.RT_SEG_LITERAL | rt.RT_SEG_NO_CHUNKS, None), (0, 4), (0, 1), (rt.RT_SEG_LITERAL, 3),
+                                         (SEQ, None), (SEQ | rt.RT_SEG_LITERAL, None), (SEQ | rt.RT_SEG_NO_CHUNKS, None), (SEQ, 4),
+                                         (SEQ, 1)])
 @pytest.mark.parametrize("n_azim,delta", [(8, 0.02), (16, 0.08), (32, 0.01), (4, 0.8)])
 def test_pincell_segments_match_oracle(pincell_model, n_azim, delta, flags, chunk):
     otg, tg = run_both(pincell_model, n_azim, delta, flags=flags, chunk_segments=chunk)
@@ -120,6 +127,11 @@ def test_pincell_segments_match_oracle(pincell_model, n_azim, delta, flags, chun
     assert_segments_equal(otg, tg)
     assert_volumes_close(otg, tg)
     assert otg.bad_status == 0
+    if not flags & SEQ:  # the other self-verifying pipeline (one thread per segment)
+        otg, tg = run_both(pincell_model, n_azim, delta, flags=flags, chunk_segments=chunk, pipeline=2)
+        assert_segments_equal(otg, tg)
+        assert_volumes_close(otg, tg)
+        assert tg.info("verify_fallbacks") == 0
 
 
 def test_reference_invariants_on_gpu_result(pincell_model):  # test/runtests.jl:30-43
@@ -144,9 +156,17 @@ def test_jittered_mesh_matches_oracle(seed, n, n_azim, delta):
     assert_volumes_close(otg, tg)
     st = tg.stats()
     assert st["fast_transitions"] > 0.8 * tg.n_segments
+    assert tg.info("verify_fallbacks") == 0
     otg, tg = run_both(model, n_azim, delta, chunk_segments=5)  # many tiny chunks: exercises every hand-off rule
     assert_segments_equal(otg, tg)
     assert_volumes_close(otg, tg)
+    otg, tg = run_both(model, n_azim, delta, flags=SEQ, chunk_segments=5)  # the sequential kernels on the same input
+    assert_segments_equal(otg, tg)
+    assert_volumes_close(otg, tg)
+    otg, tg = run_both(model, n_azim, delta, chunk_segments=5, pipeline=2)  # one thread per segment
+    assert_segments_equal(otg, tg)
+    assert_volumes_close(otg, tg)
+    assert tg.info("verify_fallbacks") == 0
 
 
 def test_offset_domain_and_rectangle():
@@ -315,3 +335,29 @@ def test_shared_reciprocal_division_is_ieee(pincell_model, exp_span):
     bad = C.c_int64(-1)
     _lib.check(tg._ctx, _lib.lib().rt_selftest_division(tg._ctx, 1 << 22, 12345 + exp_span, exp_span, C.byref(bad)))
     assert bad.value == 0
+
+
+def test_two_stage_pipeline_falls_back_to_sequential(pincell_model):
+    """a failed verification in k_eval restarts the call with the sequential kernels; the result is the same"""
+    mesh = rt.Mesh(pincell_model)
+    otg = OracleTrackGenerator(OracleMesh.from_mesh(mesh), 16, 0.02).trace().segmentize(check=False, nthreads=8)
+    tg = rt.TrackGenerator(mesh, 16, 0.02)
+    rt.trace_(tg)
+    rt.segmentize_(tg, check=False)
+    assert_segments_equal(otg, tg)
+    for pipeline in (0, 2):
+        tg.set_option("pipeline", pipeline)
+        tg.set_option("debug_verify_fail", 0)
+        rt.segmentize_(tg, check=False)
+        assert tg.info("verify_fallbacks") == 0 and (tg.info("eval_ms") > 0) == (pipeline == 2)
+        assert_segments_equal(otg, tg)
+        tg.set_option("debug_verify_fail", 1)
+        rt.segmentize_(tg, check=False)
+        assert tg.info("verify_fallbacks") == 1
+        assert_segments_equal(otg, tg)
+        assert_volumes_close(otg, tg)
+    tg.set_option("debug_verify_fail", 0)
+    tg.set_option("pipeline", 1)
+    rt.segmentize_(tg, check=False)
+    assert tg.info("verify_fallbacks") == 0 and tg.info("eval_ms") == 0
+    assert_segments_equal(otg, tg)

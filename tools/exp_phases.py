@@ -23,6 +23,7 @@ def run(label, flags=0, reps=3, **opts):
     tg.set_option("chunk_segments", opts.get("chunk_segments", 64))
     tg.set_option("target_walkers", opts.get("target_walkers", 148 * 2048 * 4))
     tg.set_option("order_grid", opts.get("order_grid", 16))
+    tg.set_option("pipeline", opts.get("pipeline", 0))
     best = None
     for _ in range(reps):
         tg.timer_start()
@@ -36,7 +37,11 @@ def run(label, flags=0, reps=3, **opts):
           f"  nseg {tg.n_segments}  seg/s {tg.n_segments / best[0] * 1e3:.3e}  fast {st['fast_transitions']:.0f} lit {st['literal_iterations']:.0f}")
 
 
-run("default")
+run("default (hybrid)")
+print("fallbacks", tg.info("verify_fallbacks"))
+run("two-stage", pipeline=2)
+print("eval_ms", tg.info("eval_ms"), "fallbacks", tg.info("verify_fallbacks"))
+run("sequential", rt.RT_SEG_SEQUENTIAL)
 if os.environ.get("RT_EXP_QUICK"):
     for og in (0, 4, 8, 32, 64, 128):
         run(f"order_grid={og}", order_grid=og)
