@@ -26,6 +26,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# segmentize!(tg; rtol): with the default rtol = sqrt(eps) the reference's own length check (src/track.jl:171-175) throws on 88
+# corner tracks of cfg3 (it drops a 2e-8 chord); 1e-6 -- the remedy its error message suggests -- lets every track complete.
+RTOL = 1e-6
+
 
 def load_workload(name, n_gpus):
     import raytracing_jl_b200 as rt
@@ -99,7 +103,7 @@ def cpu_sample(model, n_azim, delta, budget_segments=3.0e7, blocks=16, threads=N
         u0 = 1 + int(b * (n - per) / max(blocks - 1, 1)) if frac < 1.0 else 1 + b * (n // blocks)
         u1 = u0 + per if frac < 1.0 else (n + 1 if b == blocks - 1 else 1 + (b + 1) * (n // blocks))
         t0 = time.perf_counter()
-        otg.segmentize(uid_begin=u0, uid_end=u1, nthreads=threads, fetch=False, check=False)
+        otg.segmentize(rtol=RTOL, uid_begin=u0, uid_end=u1, nthreads=threads, fetch=False, check=False)
         secs += time.perf_counter() - t0
         segs += otg.n_segments
         otg.free_segments()
@@ -135,7 +139,7 @@ def workload_config(args, model, n_azim, delta):
              "cfg2": "BASELINE.json configs[1]: synthetic 4x4 BWR pin lattice", "pincell": "BASELINE.json configs[0]: demo/pincell",
              "cfg4": "BASELINE.json configs[3]: synthetic 17x17 pin lattice", "cfg5": "BASELINE.json configs[4]: synthetic 51x51 pin lattice"}
     return {"workload": names.get(args.workload, args.workload), "n_cells": int(model.num_cells), "n_nodes": int(model.num_nodes),
-            "n_azim": n_azim, "delta": delta, "bcs": "reflective", "sharding": f"uid ranges over {args.gpus} GPU(s), mesh replicated",
+            "n_azim": n_azim, "delta": delta, "rtol": RTOL, "bcs": "reflective", "sharding": f"uid ranges over {args.gpus} GPU(s), mesh replicated",
             "l2": "inputs larger than L2: cell+edge records 160 B/cell and >2 GB of segment output stream through the 126 MB L2 every step"}
 
 
@@ -181,7 +185,7 @@ def main():
         torch.cuda.synchronize()
 
     def step():
-        rt.segmentize_(tg, check=False, fetch_volumes=False)
+        rt.segmentize_(tg, rtol=RTOL, check=False, fetch_volumes=False)
 
     for _ in range(args.warmup):
         step()
@@ -230,14 +234,15 @@ def main():
         def e2e_step():
             tg.upload_mesh()  # H2D of the flattened model + device preparation
             rt.trace_(tg)
-            rt.segmentize_(tg, check=False)  # includes the D2H of volumes
+            rt.segmentize_(tg, rtol=RTOL, check=False)  # includes the D2H of volumes
             tg.segment_offsets
             return tg.fetch_segments(pinned=True)  # D2H of every Segment record into pinned host buffers
 
-        e2e_step()
+        for _ in range(2):  # the first call allocates the pinned host buffers
+            e2e_step()
         barrier()
         t0 = time.perf_counter()
-        n_e2e = 2
+        n_e2e = 3
         for _ in range(n_e2e):
             seg = e2e_step()
         torch.cuda.synchronize()
