@@ -15,7 +15,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SO_PATH = os.environ.get("RT_B200_LIB") or os.path.join(_PKG, "librt_b200.so")  # RT_B200_LIB: an alternative build
 _CSRC = os.path.join(_PKG, "csrc")
-_SOURCES = ["rt_b200.cu", "geom.cuh", "mesh_dev.cuh", "walk.cuh", "topo.cuh", "trace.cuh", "scan.cuh"]
+_SOURCES = ["rt_b200.cu", "geom.cuh", "mesh_dev.cuh", "walk.cuh", "topo.cuh", "eval.cuh", "trace.cuh", "scan.cuh"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

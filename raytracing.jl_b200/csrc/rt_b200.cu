@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "scan.cuh"
+#include "eval.cuh"
 #include "topo.cuh"
 #include "trace.cuh"
 
@@ -74,7 +75,7 @@ struct rt_ctx {
     DevBuf b_count, b_status, b_offsets, b_tile, b_vol, b_voln, b_counters, b_bad;
     DevBuf b_nch, b_blk_chunks, b_unit_base, b_unit_block, b_ch_i, b_ch_d;  // chunk plan (walk.cuh ChunkPlan)
     DevBuf b_order, b_okeys, b_ohist;  // spatial execution order of the units
-    DevBuf b_evalblk;
+    DevBuf b_evalblk, b_trkrec;
     DevBuf b_rec, b_verify, b_tsum;    // two-stage pipeline: per-segment records, verification flag, per-track length sums
     int opt_pipeline = 0;              // 0: hybrid (sign-test count walk + geometric fill walk), 1: sequential (walk.cuh only),
                                        // 2: two-stage (sign-test walks + one thread per segment); 0 and 2 fall back to 1
@@ -83,6 +84,8 @@ struct rt_ctx {
     double eval_ms = 0.0;
     cudaEvent_t ev2[2] = {nullptr, nullptr};
     int opt_order_grid = 16;           // G x G tiles (0: identity order)
+    int n_sm = 148;
+    int opt_eval_waves = 1;            // k_eval2 grid = n_sm * resident blocks * this
     long long n_units = 0;
     double opt_chunk_segments = 64.0;               // minimum expected segments per chunk
     double opt_target_walkers = 148.0 * 2048.0 * 4.0;  // chunks are sized so that about this many walkers exist
@@ -164,6 +167,8 @@ extern "C" int rt_create(rt_ctx **out, int device) {
     if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) return RT_ERR_CUDA;  // no CPU fallback
     rt_ctx *ctx = new rt_ctx();
     ctx->device = device;
+    cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
+    if (ctx->n_sm <= 0) ctx->n_sm = 148;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev[0]) != cudaSuccess || cudaEventCreate(&ctx->ev[1]) != cudaSuccess ||
         cudaEventCreate(&ctx->tev[0]) != cudaSuccess || cudaEventCreate(&ctx->tev[1]) != cudaSuccess ||
@@ -186,7 +191,7 @@ extern "C" void rt_destroy(rt_ctx *ctx) {
                      &ctx->b_voln,    &ctx->b_counters,   &ctx->b_bad,      &ctx->b_seg_d,   &ctx->b_seg_e,
                      &ctx->b_twin,    &ctx->b_he,         &ctx->b_node_reach,
                      &ctx->b_nch,     &ctx->b_blk_chunks, &ctx->b_unit_base, &ctx->b_unit_block, &ctx->b_ch_i, &ctx->b_ch_d,
-                     &ctx->b_order,   &ctx->b_okeys,      &ctx->b_ohist,     &ctx->b_rec,     &ctx->b_verify,    &ctx->b_tsum,      &ctx->b_evalblk};
+                     &ctx->b_order,   &ctx->b_okeys,      &ctx->b_ohist,     &ctx->b_rec,     &ctx->b_verify,    &ctx->b_tsum,      &ctx->b_evalblk,   &ctx->b_trkrec};
     for (DevBuf *b : all) release(*b);
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
     if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
@@ -819,6 +824,11 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         E.status = P.status;
         E.tsum = P.tsum;
         E.rtol = rtol;
+        if (topo) {
+            CK(ensure(ctx->b_trkrec, sizeof(TrackRec) * nn));
+            k_track_recs<<<blocks_for(n, 256), 256, 0, st>>>(E, n, (TrackRec *)ctx->b_trkrec.p);
+            launches += 1;
+        }
         std::vector<long long> h_off;
         if (total > cap) {
             h_off.resize((size_t)n + 1);
@@ -853,10 +863,13 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
                 E.n_seg = nseg_b;
                 CK(cudaEventRecord(ctx->ev2[0], st));
                 if (nseg_b > 0) {
-                    const long long n_eb = (nseg_b + kEvalPerBlock - 1) / kEvalPerBlock;
-                    CK(ensure(ctx->b_evalblk, sizeof(long long) * (size_t)n_eb));
-                    k_eval_blocks<<<blocks_for(n_eb, 256), 256, 0, st>>>(E, n_eb, (long long *)ctx->b_evalblk.p);
-                    k_eval<<<(unsigned)n_eb, kEvalThreads, 0, st>>>(E, (const long long *)ctx->b_evalblk.p);
+                    const long long n_groups = (nseg_b + kEvalGroup - 1) / kEvalGroup;
+                    CK(ensure(ctx->b_evalblk, sizeof(int) * (size_t)n_groups));
+                    k_eval_groups<<<blocks_for(n_groups, 256), 256, 0, st>>>(E, n_groups, (int *)ctx->b_evalblk.p);
+                    const long long eb_max = (long long)ctx->n_sm * RT_EVAL_MIN_BLOCKS * ctx->opt_eval_waves;
+                    const unsigned eblocks = (unsigned)std::min<long long>(blocks_for(n_groups, kEval2Threads / 32), eb_max);
+                    k_eval2<<<eblocks, kEval2Threads, 0, st>>>(
+                        E, (const TrackRec *)ctx->b_trkrec.p, (const int *)ctx->b_evalblk.p, n_groups);
                 }
                 CK(cudaEventRecord(ctx->ev2[1], st));
                 k_track_status<<<blocks_for(e - b, 128), 128, 0, st>>>(E);
@@ -1216,6 +1229,8 @@ extern "C" int rt_set_option(rt_ctx *ctx, const char *name, double value) {
         ctx->opt_order_grid = (int)value;
     else if (n == "pipeline" && (value == 0.0 || value == 1.0 || value == 2.0))
         ctx->opt_pipeline = (int)value;
+    else if (n == "eval_waves" && value >= 1.0 && value <= 64.0)
+        ctx->opt_eval_waves = (int)value;
     else if (n == "debug_verify_fail")
         ctx->opt_debug_verify_fail = value != 0.0;
     else

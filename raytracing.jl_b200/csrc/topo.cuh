@@ -11,7 +11,7 @@
 //   k_topo<true>   fill pass, stage 1: the same walk writes one 4-byte record per segment at its final position:
 //                  fast:  (h << 2) | (exit1 << 1)   h = entry half-edge 3*cell + k, exit1: leaves through edge k+1 (else k+2)
 //                  literal: (cell << 2) | 1
-//   k_eval         fill pass, stage 2: ONE THREAD PER SEGMENT, coalesced.  Fast records: p and q are the reference's
+//   k_eval2        (eval.cuh) fill pass, stage 2: ONE THREAD PER SEGMENT, coalesced.  Fast records: p and q are the reference's
 //                  intersection() of the track with the entry and exit edge lines (precomputed general_form, bit-identical
 //                  to the sequential path); literal records: the reference's intersections() on the cell.  It also checks
 //                  the three conditions of the sequential fast path that need the geometry (exit edge not parallel,
@@ -32,6 +32,25 @@ __device__ __forceinline__ void stg256_stream_i(void *p, unsigned long long pol,
     asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
                  "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "l"(pol)
                  : "memory");
+}
+
+// scalar loads / stores with L2 eviction policies (see walk.cuh): the node and cell tables are re-read by every segment
+// (evict_last), the per-segment records and the Segment columns pass through once (evict_first)
+__device__ __forceinline__ int ldg_i32_pol(const int *p, unsigned long long pol) {
+    int v;
+    asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double2 ldg_f64x2_pol(const double2 *p, unsigned long long pol) {
+    double2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void stg_f64_pol(double *p, double v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stg_i32_pol(int *p, int v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
 }
 
 // exit point of cell `c` through its local edge k: the reference's intersection() with that edge's line
@@ -310,104 +329,6 @@ struct EvalParams {
     double *tsum;  // per track: sum of segment lengths (atomics)
     double rtol;
 };
-
-constexpr int kEvalThreads = 256;
-constexpr int kEvalPerWarp = 31;  // lane 0 of every warp re-evaluates the exit of the previous segment (hand-over to lane 1)
-constexpr int kEvalPerBlock = kEvalPerWarp * (kEvalThreads / 32);
-
-// first track of every k_eval block (bisection of the offsets table), so that k_eval itself needs no search
-__global__ void k_eval_blocks(const __grid_constant__ EvalParams P, long long n_blocks, long long *blk_track) {
-    long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (b >= n_blocks) return;
-    long long s0 = b * kEvalPerBlock - 1 + P.offset_base;  // the block's first evaluated segment is the one before its range
-    if (s0 < P.offset_base) s0 = P.offset_base;
-    long long lo = P.trk_begin, hi = P.trk_end;  // invariant: offsets[lo] <= s0 < offsets[hi]
-    while (hi - lo > 1) {
-        long long mid = (lo + hi) >> 1;
-        if (P.offsets[mid] <= s0)
-            lo = mid;
-        else
-            hi = mid;
-    }
-    blk_track[b] = lo;
-}
-
-__global__ void __launch_bounds__(kEvalThreads) k_eval(const __grid_constant__ EvalParams P, const long long *blk_track) {
-    const unsigned FULL = 0xffffffffu;
-    const DevMesh &m = P.m;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // lanes 1..31 own the segments [w0, w0 + 31); lane 0 looks at segment w0 - 1 only to hand its exit point to lane 1
-    const long long w0 = blockIdx.x * (long long)kEvalPerBlock + warp * kEvalPerWarp;
-    if (w0 >= P.n_seg) return;  // whole warp
-    const long long s = w0 + lane - 1;
-    const bool exists = s >= 0 && s < P.n_seg;
-    const bool live = exists && lane > 0;
-    const long long sg = (s < 0 ? 0 : (s >= P.n_seg ? P.n_seg - 1 : s)) + P.offset_base;  // shard-global segment index
-    long long t = blk_track[blockIdx.x];
-    while (P.offsets[t + 1] <= sg) ++t;  // (also skips empty tracks)
-    const int az = P.t.azim[t];
-    const Line trk{P.t.a[t], P.t.b[t], P.t.c[t]};
-    const bool right = P.ang.phi[az] < kPi / 2;
-    const int r = exists ? P.rec[sg - P.offset_base] : 1;
-    const bool fast = (r & 1) == 0;  // literal records were written by k_topo<true>
-    const int h = r >> 2;
-    const int cell = fast ? h / 3 : h;
-    const int kin = fast ? h - 3 * cell : 0;
-    const bool exit1 = (r & 2) != 0;
-    int kout = kin + (exit1 ? 1 : 2);
-    kout = kout >= 3 ? kout - 3 : kout;
-    P2 p, q;
-    q.x = q.y = 0.0;
-    bool par_out = false;
-    // The edge lines are evaluated from the node coordinates (general_form, src/intersection.jl:11-18,57: the same formula, in
-    // the cell's stored orientation, that produced the EdgeRec table): the node table is ~10x smaller than the edge-line table
-    // and stays in L2, whereas one 32-byte EdgeRec per segment is a random HBM access.
-    const int *cn = m.cell_nodes + 3 * cell;
-    const int kn = kout == 2 ? 0 : kout + 1;
-    if (fast) {
-        const double2 a = m.xy[cn[kout]], b = m.xy[cn[kn]];
-        par_out = intersection(trk, general_form_shared(P2{a.x, a.y}, P2{b.x, b.y}), q);
-    }
-    // hand-over: lane i-1's exit is my entry iff it is the previous segment of the same track and a fast record (consecutive
-    // fast records of one track are always edge-adjacent; the shared edge gives the same line up to an exact sign flip)
-    const double upx = __shfl_up_sync(FULL, q.x, 1), upy = __shfl_up_sync(FULL, q.y, 1);
-    const int up_fast = __shfl_up_sync(FULL, (int)(fast && exists), 1);
-    const long long up_t = __shfl_up_sync(FULL, t, 1);
-    double l = 0.0;
-    if (fast && live) {
-        if (up_fast && up_t == t) {
-            p.x = upx;
-            p.y = upy;
-        } else {  // first segment of a track, or the previous record is literal
-            const int ki2 = kin == 2 ? 0 : kin + 1;
-            const double2 a = m.xy[cn[kin]], b = m.xy[cn[ki2]];
-            intersection(trk, general_form_shared(P2{a.x, a.y}, P2{b.x, b.y}), p);  // never parallel: the previous chord ended here
-        }
-        l = norm2(p.x - q.x, p.y - q.y);  // Segment(p, q): norm(p - q), src/segment.jl:32
-        P.opx[s] = p.x;
-        P.opy[s] = p.y;
-        P.oqx[s] = q.x;
-        P.oqy[s] = q.y;
-        P.olen[s] = l;
-        P.oelem[s] = cell + 1;
-        if (P.vol) atomicAdd(&P.vol[cell], P.ang.delta_eff[az] * l);  // volumes[i] += delta_s[a]*l, src/trackgenerator.jl:382
-        // the geometric conditions of the sequential fast path (walk.cuh); k_topo's filters make them hold
-        const bool kin_lt_kout = (kin == 0) || (kin == 1 && exit1);
-        const bool in_first = right ? (kin_lt_kout ? (p.x < q.x) : !(q.x < p.x)) : (kin_lt_kout ? (p.x > q.x) : !(q.x > p.x));
-        if (par_out || !in_first || !(l > P.lmin)) atomicExch(P.verify_fail, 1);
-    }
-    // per-track sum of lengths (decides the reference's length check up to a margin, see k_track_status)
-    if (P.tsum) {
-        const long long t1 = __shfl_sync(FULL, t, 1);
-        if (__all_sync(FULL, t == t1 || lane == 0)) {
-            double v = l;
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
-            if (lane == 0) atomicAdd(&P.tsum[t1], v);
-        } else if (fast && live) {
-            atomicAdd(&P.tsum[t], l);
-        }
-    }
-}
 
 // isapprox(track.l, sum(l.(segments)); rtol)  src/track.jl:171-175.  The atomically accumulated sum differs from the
 // reference's left-to-right sum by at most ~n*eps relative; only when the comparison is that close to its threshold is the

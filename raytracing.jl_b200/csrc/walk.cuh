@@ -232,6 +232,7 @@ __device__ __forceinline__ void stg128_stream(void *p, unsigned long long pol, i
 }
 
 constexpr int kWalkThreads = 128;
+constexpr int kStage = 8;  // fill pass: staged segments per thread (a ring; complete aligned quads are flushed at warp-uniform points)
 // resident blocks per SM the register allocator must allow (without it ptxas picks ~56-72 registers and spills the walk state)
 #ifndef RT_WALK_MIN_BLOCKS
 #define RT_WALK_MIN_BLOCKS 4
@@ -322,9 +323,11 @@ template <bool FILL>
 __global__ void __launch_bounds__(kWalkThreads, RT_WALK_MIN_BLOCKS) k_walk(const __grid_constant__ WalkParams P) {
     const unsigned FULL = 0xffffffffu;
     const DevMesh &m = P.m;
-    // fill pass: every thread stages 4 consecutive segments and writes them as full, aligned 32-byte sectors
-    __shared__ double s_buf[FILL ? 5 * 4 * kWalkThreads : 1];
-    __shared__ int s_el[FILL ? 4 * kWalkThreads : 1];
+    // fill pass: every thread stages its segments in a ring of kStage slots and writes complete, aligned groups of four as full
+    // 32-byte sectors; the flushes happen at points that are uniform across the warp (every fourth fast iteration and once per
+    // outer iteration), so the lanes of a warp execute them together although their output positions differ modulo 4
+    __shared__ double s_buf[FILL ? 5 * kStage * kWalkThreads : 1];
+    __shared__ int s_el[FILL ? kStage * kWalkThreads : 1];
     const int tid = threadIdx.x;
     long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
@@ -426,39 +429,58 @@ __global__ void __launch_bounds__(kWalkThreads, RT_WALK_MIN_BLOCKS) k_walk(const
         }
     }
 
+    long long wpos = out;  // fill pass: every staged segment before this output position has been written
+    // write the complete aligned quads among the staged segments [wpos, out + nseg); all = true: everything (chunk end)
+    auto flush = [&](bool all) {
+        if (!FILL) return;
+        const long long o_next = out + nseg;
+        const long long head = (wpos + 3) & ~3LL;  // unaligned chunk start: scalar stores up to the first sector boundary
+        const long long stop = all ? o_next : (o_next & ~3LL);
+        if ((wpos & 3) && head <= stop) {
+            for (; wpos < head; ++wpos) {
+                const int kk = (int)(wpos & (kStage - 1));
+                P.opx[wpos] = s_buf[(0 * kStage + kk) * kWalkThreads + tid];
+                P.opy[wpos] = s_buf[(1 * kStage + kk) * kWalkThreads + tid];
+                P.oqx[wpos] = s_buf[(2 * kStage + kk) * kWalkThreads + tid];
+                P.oqy[wpos] = s_buf[(3 * kStage + kk) * kWalkThreads + tid];
+                P.olen[wpos] = s_buf[(4 * kStage + kk) * kWalkThreads + tid];
+                P.oelem[wpos] = s_el[kk * kWalkThreads + tid];
+            }
+        }
+        while (!(wpos & 3) && wpos + 4 <= stop) {
+            const int k0 = (int)(wpos & (kStage - 1));
+            double *dst[5] = {P.opx, P.opy, P.oqx, P.oqy, P.olen};
+#pragma unroll
+            for (int a = 0; a < 5; ++a)
+                stg256_stream(dst[a] + wpos, pol_stream, s_buf[(a * kStage + k0 + 0) * kWalkThreads + tid],
+                              s_buf[(a * kStage + k0 + 1) * kWalkThreads + tid], s_buf[(a * kStage + k0 + 2) * kWalkThreads + tid],
+                              s_buf[(a * kStage + k0 + 3) * kWalkThreads + tid]);
+            stg128_stream(P.oelem + wpos, pol_stream, s_el[(k0 + 0) * kWalkThreads + tid], s_el[(k0 + 1) * kWalkThreads + tid],
+                          s_el[(k0 + 2) * kWalkThreads + tid], s_el[(k0 + 3) * kWalkThreads + tid]);
+            wpos += 4;
+        }
+        if (all) {
+            for (; wpos < o_next; ++wpos) {
+                const int kk = (int)(wpos & (kStage - 1));
+                P.opx[wpos] = s_buf[(0 * kStage + kk) * kWalkThreads + tid];
+                P.opy[wpos] = s_buf[(1 * kStage + kk) * kWalkThreads + tid];
+                P.oqx[wpos] = s_buf[(2 * kStage + kk) * kWalkThreads + tid];
+                P.oqy[wpos] = s_buf[(3 * kStage + kk) * kWalkThreads + tid];
+                P.olen[wpos] = s_buf[(4 * kStage + kk) * kWalkThreads + tid];
+                P.oelem[wpos] = s_el[kk * kWalkThreads + tid];
+            }
+        }
+    };
+
     auto push = [&](int e, double ax, double ay, double bx, double by, double l) {
         if (FILL) {
-            long long o = out + nseg;
-            int k = (int)(o & 3);
-            s_buf[(0 * 4 + k) * kWalkThreads + tid] = ax;
-            s_buf[(1 * 4 + k) * kWalkThreads + tid] = ay;
-            s_buf[(2 * 4 + k) * kWalkThreads + tid] = bx;
-            s_buf[(3 * 4 + k) * kWalkThreads + tid] = by;
-            s_buf[(4 * 4 + k) * kWalkThreads + tid] = l;
+            const int k = (int)((out + nseg) & (kStage - 1));
+            s_buf[(0 * kStage + k) * kWalkThreads + tid] = ax;
+            s_buf[(1 * kStage + k) * kWalkThreads + tid] = ay;
+            s_buf[(2 * kStage + k) * kWalkThreads + tid] = bx;
+            s_buf[(3 * kStage + k) * kWalkThreads + tid] = by;
+            s_buf[(4 * kStage + k) * kWalkThreads + tid] = l;
             s_el[k * kWalkThreads + tid] = e + 1;
-            bool last = nseg + 1 >= limit;
-            if (k == 3 || last) {
-                long long g0 = o & ~3LL;
-                int kf = (int)((g0 > out ? g0 : out) - g0);
-                if (kf == 0 && k == 3) {
-                    double *dst[5] = {P.opx, P.opy, P.oqx, P.oqy, P.olen};
-#pragma unroll
-                    for (int a = 0; a < 5; ++a)
-                        stg256_stream(dst[a] + g0, pol_stream, s_buf[(a * 4 + 0) * kWalkThreads + tid], s_buf[(a * 4 + 1) * kWalkThreads + tid],
-                                      s_buf[(a * 4 + 2) * kWalkThreads + tid], s_buf[(a * 4 + 3) * kWalkThreads + tid]);
-                    stg128_stream(P.oelem + g0, pol_stream, s_el[0 * kWalkThreads + tid], s_el[1 * kWalkThreads + tid],
-                                  s_el[2 * kWalkThreads + tid], s_el[3 * kWalkThreads + tid]);
-                } else {
-                    for (int kk = kf; kk <= k; ++kk) {
-                        P.opx[g0 + kk] = s_buf[(0 * 4 + kk) * kWalkThreads + tid];
-                        P.opy[g0 + kk] = s_buf[(1 * 4 + kk) * kWalkThreads + tid];
-                        P.oqx[g0 + kk] = s_buf[(2 * 4 + kk) * kWalkThreads + tid];
-                        P.oqy[g0 + kk] = s_buf[(3 * 4 + kk) * kWalkThreads + tid];
-                        P.olen[g0 + kk] = s_buf[(4 * 4 + kk) * kWalkThreads + tid];
-                        P.oelem[g0 + kk] = s_el[kk * kWalkThreads + tid];
-                    }
-                }
-            }
         }
         if (P.vol) atomicAdd(&P.vol[e], P.ang.delta_eff[az] * l);  // volumes[i] += delta_s[a]*l, src/trackgenerator.jl:382
         sum += l;
@@ -499,14 +521,17 @@ __global__ void __launch_bounds__(kWalkThreads, RT_WALK_MIN_BLOCKS) k_walk(const
                 // reversing the edge negates (A, B, C) exactly and intersection() is invariant under that negation bit for bit.
                 const double A = ky - ay, B = ax - kx, C = kx * ay - ax * ky;
                 const Recip rn = recip_prepare(sqrt(A * A + B * B + C * C));
-                const double La = div_shared(A, rn), Lb = div_shared(B, rn), Lc = div_shared(C, rn);
+                // (the quotients are only used if `dok` stays true: otherwise the transition is left to the literal walk)
+                bool dok = rn.ok;
+                const double La = div_try<true>(A, rn, dok), Lb = div_try<true>(B, rn, dok), Lc = div_try<true>(C, rn, dok);
                 // intersection(track.ABC, L), src/intersection.jl:127-138 (operands are finite here, so isapprox(a, b) reduces
                 // to |a - b| <= rtol * max(|a|, |b|))
                 const double a = tb * La, b = Lb * ta;
                 const double fa = fabs(a), fb = fabs(b);
                 const bool par = fabs(a - b) <= kRtol * (fa > fb ? fa : fb);
                 const Recip rd = recip_prepare(a - b);
-                const double Xx = div_shared(tc * Lb - Lc * tb, rd), Xy = div_shared(ta * Lc - La * tc, rd);
+                dok = dok && rd.ok;
+                const double Xx = div_try<false>(tc * Lb - Lc * tb, rd, dok), Xy = div_try<false>(ta * Lc - La * tc, rd, dok);
                 const int kin = (enc >> 1) & 3;
                 // int_points are stored in edge-index order; order_intersection_points (src/intersection.jl:151-159) must put
                 // the entry point first
@@ -514,7 +539,7 @@ __global__ void __launch_bounds__(kWalkThreads, RT_WALK_MIN_BLOCKS) k_walk(const
                 const bool in_first = right ? (kin_lt_kout ? (qx < Xx) : !(Xx < qx)) : (kin_lt_kout ? (qx > Xx) : !(Xx > qx));
                 const double dx = qx - Xx, dy = qy - Xy;
                 const double l = sqrt(dx * dx + dy * dy);  // Segment(p, q): norm(p - q), src/segment.jl:32
-                bool accept = clear_ok && !par && in_first && l > P.lmin;
+                bool accept = dok && clear_ok && !par && in_first && l > P.lmin;
                 // cells touching the bounding-box band: the re-location points must not be `inboundary`
                 if (clearf < 0.0f && accept) accept = bbox_dist(m, qx, qy) > 0.25 * l + 8.0 * P.tiny;
                 // the walker state needed only by the next fast transition is updated unconditionally (the literal path re-arms it)
@@ -538,7 +563,9 @@ __global__ void __launch_bounds__(kWalkThreads, RT_WALK_MIN_BLOCKS) k_walk(const
                 }
             }
             if (!ok) mode = MODE_SLOW;  // re-locate literally from advance_step(q, tiny, phi), src/track.jl:165-166
+            if ((it & 3) == 3) flush(false);
         }
+        flush(false);
         // ------------------------------------------------------------------ LITERAL phase (until one push)
         if (mode == MODE_SLOW) {
             // advance_step: x + step*Point2D(cos phi, sin phi), src/point.jl:43
@@ -568,6 +595,7 @@ __global__ void __launch_bounds__(kWalkThreads, RT_WALK_MIN_BLOCKS) k_walk(const
         }
     }
 
+    flush(true);
     if (!FILL && t < P.n_tracks && j < P.ch.nch[t]) {
         P.ch.count[cidx] = active ? nseg : 0;
         P.ch.sum[cidx] = sum;

@@ -206,9 +206,10 @@ def test_structured_mesh_exact_vertex_crossings():
     assert_segments_equal(otg, tg)
 
 
+@pytest.mark.parametrize("pipeline", [0, 1, 2])
 @pytest.mark.parametrize("chunk", [None, 7])
-def test_batched_fill_equals_single_shot(pincell_model, chunk):
-    otg, tg = run_both(pincell_model, 32, 0.01, capacity=20000, chunk_segments=chunk)
+def test_batched_fill_equals_single_shot(pincell_model, chunk, pipeline):
+    otg, tg = run_both(pincell_model, 32, 0.01, capacity=20000, chunk_segments=chunk, pipeline=pipeline)
     assert tg.n_segments == otg.n_segments and np.array_equal(tg.segment_offsets, otg.seg_offsets)
     # only the last batch is resident: compare it with the tail of the oracle's arrays
     s = tg.segments

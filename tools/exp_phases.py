@@ -24,6 +24,7 @@ def run(label, flags=0, reps=3, **opts):
     tg.set_option("target_walkers", opts.get("target_walkers", 148 * 2048 * 4))
     tg.set_option("order_grid", opts.get("order_grid", 16))
     tg.set_option("pipeline", opts.get("pipeline", 0))
+    tg.set_option("eval_waves", opts.get("eval_waves", int(os.environ.get("RT_EVAL_WAVES", "1"))))
     best = None
     for _ in range(reps):
         tg.timer_start()
@@ -41,6 +42,11 @@ run("default (hybrid)")
 print("fallbacks", tg.info("verify_fallbacks"))
 run("two-stage", pipeline=2)
 print("eval_ms", tg.info("eval_ms"), "fallbacks", tg.info("verify_fallbacks"))
+if os.environ.get("RT_EXP_MIN"):
+    for w in (2, 4, 8):
+        run(f"two-stage eval_waves={w}", pipeline=2, eval_waves=w)
+        print("eval_ms", tg.info("eval_ms"))
+    sys.exit(0)
 run("sequential", rt.RT_SEG_SEQUENTIAL)
 if os.environ.get("RT_EXP_QUICK"):
     for og in (0, 4, 8, 32, 64, 128):
