@@ -53,37 +53,68 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The timed region of the default run
+    is only tens of milliseconds, so the clocks are polled through NVML every 2 ms from a thread of this process (nvidia-smi
+    -lms cannot sample faster than ~100 ms); nvidia-smi is the fallback when NVML is unavailable."""
 
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.sm, self.reasons, self.mx = index, [], set(), None
+        self._stop, self._thr, self.how = threading.Event(), None, None
+
+    def _nvml_loop(self):
+        import pynvml as nv
+
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            for name, bit in bits.items():
+                if r & bit:
+                    self.reasons.add(name)
+            time.sleep(0.002)
+
+    def _smi_loop(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.sm.append(float(out[0]))
+                self.mx = float(out[1])
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(name)
+            except Exception:
+                return
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml as nv
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            nv.nvmlInit()
+            # NVML indexes physical devices: honour CUDA_VISIBLE_DEVICES when it lists ordinals
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [int(v) for v in vis.split(",") if v.strip().isdigit()]
+            if ids and self.index < len(ids):
+                self.index = ids[self.index]
+            self.how, target = "nvml 2 ms", self._nvml_loop
+        except Exception:
+            self.how, target = "nvidia-smi", self._smi_loop
+        self._thr = threading.Thread(target=target, daemon=True)
+        self._thr.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=6)
+        sm = self.sm
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                "samples": len(sm), "how": self.how}
 
 
 def cpu_sample(model, n_azim, delta, budget_segments=3.0e7, blocks=16, threads=None):
@@ -202,6 +233,9 @@ def main():
     clocks = sampler.stop()
     nseg_local = tg.n_segments
     st = tg.stats()
+    if world > 1:
+        print(f"[rank {rank}] ms/step {ms / args.steps:.3f} segments {nseg_local} phases "
+              f"{ {k: round(float(np.mean([p[k] for p in phases])), 3) for k in phases[0]} }", file=sys.stderr)
     t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     n_all = torch.tensor([float(nseg_local), float(tg.uid_end - tg.uid_begin)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -238,7 +272,8 @@ def main():
             tg.segment_offsets
             return tg.fetch_segments(pinned=True)  # D2H of every Segment record into pinned host buffers
 
-        for _ in range(2):  # the first call allocates the pinned host buffers
+        tg.pin_mesh()  # inputs of the step live in pinned host memory
+        for _ in range(2):  # the first call allocates the pinned host buffers of the results
             e2e_step()
         barrier()
         t0 = time.perf_counter()

@@ -297,12 +297,27 @@ class TrackGenerator(TrackLayout):
         self._ctx = h
         self.upload_mesh()
 
+    def pin_mesh(self):
+        """Keep the five flattened mesh arrays in page-locked host memory, so that upload_mesh() is one asynchronous DMA per
+        array at full PCIe rate (a Julia caller would register its Gridap arrays with cudaHostRegister instead)."""
+        mesh, m = self.mesh, self.mesh.model
+        src = [m.node_coordinates.reshape(-1), mesh.cell_nodes[0], mesh.cell_nodes[1], mesh.node_cells[0], mesh.node_cells[1]]
+        self._pinned_mesh = []
+        for a in src:
+            buf = _lib.PinnedArray(a.shape, a.dtype)
+            buf.array[...] = a
+            self._pinned_mesh.append(buf)
+
     def upload_mesh(self):
         """Host -> device copy of the flattened mesh + device-side preparation (rt_mesh_upload)."""
         mesh, m = self.mesh, self.mesh.model
-        _lib.check(self._ctx, _lib.lib().rt_mesh_upload(
-            self._ctx, m.num_nodes, m.node_coordinates.reshape(-1), m.num_cells, mesh.cell_nodes[0], mesh.cell_nodes[1],
-            mesh.node_cells[0], mesh.node_cells[1], mesh.bb_min, mesh.bb_max))
+        if getattr(self, "_pinned_mesh", None):
+            xy, cp, cd, np_, nd = (b.array for b in self._pinned_mesh)
+        else:
+            xy, cp, cd, np_, nd = (m.node_coordinates.reshape(-1), mesh.cell_nodes[0], mesh.cell_nodes[1], mesh.node_cells[0],
+                                   mesh.node_cells[1])
+        _lib.check(self._ctx, _lib.lib().rt_mesh_upload(self._ctx, m.num_nodes, xy, m.num_cells, cp, cd, np_, nd, mesh.bb_min,
+                                                        mesh.bb_max))
         self._traced = self._segmented = False
         self._track_data = self._segments = self._offsets = None
 
@@ -404,9 +419,10 @@ class TrackGenerator(TrackLayout):
 
     def close(self):
         if getattr(self, "_ctx", None):
-            for b in self._pinned.values():
+            for b in list(self._pinned.values()) + list(getattr(self, "_pinned_mesh", None) or []):
                 b.free()
             self._pinned = {}
+            self._pinned_mesh = None
             self._segments = None
             _lib.lib().rt_destroy(self._ctx)
             self._ctx = None
@@ -475,18 +491,54 @@ def trace_(tg: TrackGenerator) -> TrackGenerator:
     return tg
 
 
+class DeviceColumn:
+    """A device-resident column of a segment batch, consumable by torch / cupy through ``__cuda_array_interface__``."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr or 0), False), "version": 2}
+
+
+class SegmentBatch:
+    """One uid batch of Segment records as produced on the device (``rt_batch`` of include/rt_b200.h): what an on-GPU consumer
+    (a transport sweep) sees when the shard's segments do not fit in memory at once."""
+
+    def __init__(self, b):
+        self.uid_begin, self.uid_end, self.n_segments = int(b.uid_begin), int(b.uid_end), int(b.n_segments)
+        self.offset_base, self.attempt, self.stream = int(b.offset_base), int(b.attempt), b.stream
+        self.d_offsets = b.d_offsets  # device pointer: int64 offsets of the shard's tracks (n_shard + 1)
+        n = self.n_segments
+        self.px, self.py, self.qx, self.qy, self.len = (DeviceColumn(p, n, "<f8") for p in (b.d_px, b.d_py, b.d_qx, b.d_qy, b.d_len))
+        self.element = DeviceColumn(b.d_element, n, "<i4")
+
+
 def segmentize_(tg: TrackGenerator, k: int = 5, rtol: float = RTOL_DEFAULT, flags: int = 0, max_iter: int = MAX_ITER,
-                check: bool = True, fetch_volumes: bool = True) -> TrackGenerator:
-    """segmentize!(tg; k, rtol): count pass -> scan -> fill pass (+ fused fill_volumes) on the device."""
+                check: bool = True, fetch_volumes: bool = True, on_batch=None) -> TrackGenerator:
+    """segmentize!(tg; k, rtol): count pass -> scan -> fill pass (+ fused fill_volumes) on the device.
+    ``on_batch(SegmentBatch)`` is called after every uid batch of the fill pass (one batch when everything fits)."""
     L = _lib.lib()
+    cb = None
+    if on_batch is not None:
+        def _cb(bptr, _user):
+            try:
+                on_batch(SegmentBatch(bptr.contents))
+                return 0
+            except Exception as e:  # noqa: BLE001 -- reported through the return code
+                tg._batch_error = e
+                return 1
+
+        cb = _lib.BATCH_CB(_cb)
     if not tg._traced:
         raise RuntimeError("Segmentation is intended after tracing. Please, call `trace!` first!")
     tg._segmented = False
     tg._segments = tg._offsets = None
     nseg, bad_uid, bad_status = C.c_int64(0), C.c_int64(0), C.c_int32(0)
     delta = tg.azimuthal_quadrature.deltas
-    rc = L.rt_segmentize(tg._ctx, tg.tiny_step, int(k), float(rtol), int(max_iter), _lib.ptr(delta), int(flags), None, None,
+    rc = L.rt_segmentize(tg._ctx, tg.tiny_step, int(k), float(rtol), int(max_iter), _lib.ptr(delta), int(flags),
+                         C.cast(cb, C.c_void_p) if cb is not None else None, None,
                          C.byref(nseg), C.byref(bad_uid), C.byref(bad_status))
+    if on_batch is not None and getattr(tg, "_batch_error", None) is not None:
+        err, tg._batch_error = tg._batch_error, None
+        raise err
     tg.n_segments = int(nseg.value)
     tg.first_bad_uid, tg.bad_status = int(bad_uid.value), int(bad_status.value)
     if rc == -8:

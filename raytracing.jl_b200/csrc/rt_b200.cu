@@ -45,7 +45,8 @@ struct rt_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaEvent_t pev[6][2] = {};   // per phase: start/stop events; elapsed times are read lazily (rt_phase_ms, rt_stats)
+    bool pev_dirty[6] = {false, false, false, false, false, false};
     cudaEvent_t tev[2] = {nullptr, nullptr};
 
     // mesh
@@ -76,6 +77,8 @@ struct rt_ctx {
     DevBuf b_nch, b_blk_chunks, b_unit_base, b_unit_block, b_ch_i, b_ch_d;  // chunk plan (walk.cuh ChunkPlan)
     DevBuf b_order, b_okeys, b_ohist;  // spatial execution order of the units
     DevBuf b_evalblk, b_trkrec;
+    long long *h_pin = nullptr;  // page-locked scratch for the small device->host read-backs of rt_segmentize (16 words)
+    DevBuf b_scratch, b_gcounts, b_gcursor;  // rt_mesh_upload staging (kept between uploads)
     DevBuf b_rec, b_verify, b_tsum;    // two-stage pipeline: per-segment records, verification flag, per-track length sums
     int opt_pipeline = 0;              // 0: hybrid (sign-test count walk + geometric fill walk), 1: sequential (walk.cuh only),
                                        // 2: two-stage (sign-test walks + one thread per segment); 0 and 2 fall back to 1
@@ -170,12 +173,21 @@ extern "C" int rt_create(rt_ctx **out, int device) {
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (ctx->n_sm <= 0) ctx->n_sm = 148;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&ctx->ev[0]) != cudaSuccess || cudaEventCreate(&ctx->ev[1]) != cudaSuccess ||
         cudaEventCreate(&ctx->tev[0]) != cudaSuccess || cudaEventCreate(&ctx->tev[1]) != cudaSuccess ||
         cudaEventCreate(&ctx->ev2[0]) != cudaSuccess || cudaEventCreate(&ctx->ev2[1]) != cudaSuccess) {
         delete ctx;
         return RT_ERR_CUDA;
     }
+    if (cudaHostAlloc((void **)&ctx->h_pin, 16 * sizeof(long long), cudaHostAllocDefault) != cudaSuccess) {
+        delete ctx;
+        return RT_ERR_NOMEM;
+    }
+    for (int ph = 0; ph < 6; ++ph)
+        for (int q = 0; q < 2; ++q)
+            if (cudaEventCreate(&ctx->pev[ph][q]) != cudaSuccess) {
+                delete ctx;
+                return RT_ERR_CUDA;
+            }
     *out = ctx;
     return RT_OK;
 }
@@ -191,11 +203,14 @@ extern "C" void rt_destroy(rt_ctx *ctx) {
                      &ctx->b_voln,    &ctx->b_counters,   &ctx->b_bad,      &ctx->b_seg_d,   &ctx->b_seg_e,
                      &ctx->b_twin,    &ctx->b_he,         &ctx->b_node_reach,
                      &ctx->b_nch,     &ctx->b_blk_chunks, &ctx->b_unit_base, &ctx->b_unit_block, &ctx->b_ch_i, &ctx->b_ch_d,
-                     &ctx->b_order,   &ctx->b_okeys,      &ctx->b_ohist,     &ctx->b_rec,     &ctx->b_verify,    &ctx->b_tsum,      &ctx->b_evalblk,   &ctx->b_trkrec};
+                     &ctx->b_order,   &ctx->b_okeys,      &ctx->b_ohist,     &ctx->b_rec,     &ctx->b_verify,    &ctx->b_tsum,      &ctx->b_evalblk,   &ctx->b_trkrec,
+                     &ctx->b_scratch, &ctx->b_gcounts,   &ctx->b_gcursor};
     for (DevBuf *b : all) release(*b);
-    if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
-    if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
+    for (int ph = 0; ph < 6; ++ph)
+        for (int q = 0; q < 2; ++q)
+            if (ctx->pev[ph][q]) cudaEventDestroy(ctx->pev[ph][q]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     delete ctx;
 }
 
@@ -206,13 +221,20 @@ extern "C" int rt_host_alloc(void **ptr, size_t bytes) {
 }
 extern "C" int rt_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? RT_OK : RT_ERR_CUDA; }
 
-static void tic(rt_ctx *ctx) { cudaEventRecord(ctx->ev[0], ctx->stream); }
-static double toc(rt_ctx *ctx) {
-    cudaEventRecord(ctx->ev[1], ctx->stream);
-    cudaEventSynchronize(ctx->ev[1]);
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-    return (double)ms;
+// phase stopwatches: events only, no host synchronisation on the hot path
+static void tic(rt_ctx *ctx, int ph) { cudaEventRecord(ctx->pev[ph][0], ctx->stream); }
+static void toc(rt_ctx *ctx, int ph) {
+    cudaEventRecord(ctx->pev[ph][1], ctx->stream);
+    ctx->pev_dirty[ph] = true;
+}
+static void collect_phase_ms(rt_ctx *ctx) {
+    for (int ph = 0; ph < 6; ++ph) {
+        if (!ctx->pev_dirty[ph]) continue;
+        float ms = 0.f;
+        if (cudaEventSynchronize(ctx->pev[ph][1]) == cudaSuccess && cudaEventElapsedTime(&ms, ctx->pev[ph][0], ctx->pev[ph][1]) == cudaSuccess)
+            ctx->phase_ms[ph] = (double)ms;
+        ctx->pev_dirty[ph] = false;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -229,7 +251,7 @@ extern "C" int rt_mesh_upload(rt_ctx *ctx, int32_t n_nodes, const double *xy, in
             return fail(ctx, RT_ERR_ARG, "rt_mesh_upload: cell %d is not a triangle (reference src/mesh.jl:149-150)", c + 1);
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    tic(ctx);
+    tic(ctx, 0);
     size_t n_nc = (size_t)(node_cell_ptrs[n_nodes] - 1);
     CK(ensure(ctx->b_xy, sizeof(double2) * (size_t)n_nodes));
     CK(ensure(ctx->b_cell_nodes, sizeof(int) * 3 * (size_t)n_cells));
@@ -241,24 +263,20 @@ extern "C" int rt_mesh_upload(rt_ctx *ctx, int32_t n_nodes, const double *xy, in
     CK(ensure(ctx->b_qual, sizeof(float) * (size_t)n_cells));
     CK(ensure(ctx->b_bdist, sizeof(float) * (size_t)n_cells));
     CK(ensure(ctx->b_sc, sizeof(MeshScalars)));
-    // stage the 1-based tables through a scratch buffer and convert on the device
-    DevBuf scratch;
-    size_t max_tab = std::max(std::max((size_t)3 * n_cells, (size_t)n_nodes + 1), n_nc);
-    CK(ensure(scratch, sizeof(int32_t) * max_tab));
+    // stage the 1-based tables through a (persistent) scratch buffer and convert on the device; no host synchronisation here:
+    // the three tables use disjoint scratch regions
+    const size_t tab_n[3] = {(size_t)3 * n_cells, (size_t)n_nodes + 1, n_nc};
+    CK(ensure(ctx->b_scratch, sizeof(int32_t) * (tab_n[0] + tab_n[1] + tab_n[2])));
     CK(cudaMemcpyAsync(ctx->b_xy.p, xy, sizeof(double) * 2 * (size_t)n_nodes, cudaMemcpyHostToDevice, st));
-    struct {
-        const int32_t *src;
-        void *dst;
-        size_t n;
-    } tabs[3] = {{cell_data, ctx->b_cell_nodes.p, (size_t)3 * n_cells},
-                 {node_cell_ptrs, ctx->b_nc_ptrs.p, (size_t)n_nodes + 1},
-                 {node_cell_data, ctx->b_nc_data.p, n_nc}};
-    for (auto &tb : tabs) {
-        CK(cudaMemcpyAsync(scratch.p, tb.src, sizeof(int32_t) * tb.n, cudaMemcpyHostToDevice, st));
-        k_to_zero_based<<<blocks_for((long long)tb.n, 256), 256, 0, st>>>((const int32_t *)scratch.p, (int *)tb.dst, (long long)tb.n);
-        CK(cudaStreamSynchronize(st));  // host source may be pageable; scratch is reused
+    const int32_t *tab_src[3] = {cell_data, node_cell_ptrs, node_cell_data};
+    void *tab_dst[3] = {ctx->b_cell_nodes.p, ctx->b_nc_ptrs.p, ctx->b_nc_data.p};
+    size_t tab_off = 0;
+    for (int q = 0; q < 3; ++q) {
+        int32_t *stage = (int32_t *)ctx->b_scratch.p + tab_off;
+        CK(cudaMemcpyAsync(stage, tab_src[q], sizeof(int32_t) * tab_n[q], cudaMemcpyHostToDevice, st));
+        k_to_zero_based<<<blocks_for((long long)tab_n[q], 256), 256, 0, st>>>(stage, (int *)tab_dst[q], (long long)tab_n[q]);
+        tab_off += tab_n[q];
     }
-    release(scratch);
 
     DevMesh &m = ctx->m;
     m.n_nodes = n_nodes;
@@ -305,7 +323,7 @@ extern "C" int rt_mesh_upload(rt_ctx *ctx, int32_t n_nodes, const double *xy, in
     k_node_reach<<<blocks_for(n_cells, 128), 128, 0, st>>>(m, (const CellRec *)ctx->b_cells.p, (const MeshScalars *)ctx->b_sc.p,
                                                            (float *)ctx->b_node_reach.p);
     // grid: count -> scan -> fill
-    DevBuf counts, cursor;
+    DevBuf &counts = ctx->b_gcounts, &cursor = ctx->b_gcursor;
     CK(ensure(counts, sizeof(int) * n_bins));
     CK(ensure(cursor, sizeof(int) * n_bins));
     CK(cudaMemsetAsync(counts.p, 0, sizeof(int) * n_bins, st));
@@ -316,10 +334,8 @@ extern "C" int rt_mesh_upload(rt_ctx *ctx, int32_t n_nodes, const double *xy, in
     CK(cudaGetLastError());
     MeshScalars sc;
     CK(cudaMemcpyAsync(&sc, ctx->b_sc.p, sizeof(sc), cudaMemcpyDeviceToHost, st));
-    ctx->phase_ms[0] = toc(ctx);
+    toc(ctx, 0);
     CK(cudaStreamSynchronize(st));
-    release(counts);
-    release(cursor);
     ctx->smax = sc.smax;
     ctx->lmax = sc.lmax;
     ctx->edge_sum = sc.edge_sum;
@@ -445,7 +461,7 @@ extern "C" int rt_trace(rt_ctx *ctx, int32_t n_azim_2, const int64_t *n_tracks_x
     P.uid_begin = uid_begin;
     P.n = n;
     P.t = t;
-    tic(ctx);
+    tic(ctx, 1);
     DevBuf dsum;
     CK(ensure(dsum, sizeof(double)));
     CK(cudaMemsetAsync(dsum.p, 0, sizeof(double), ctx->stream));
@@ -457,7 +473,7 @@ extern "C" int rt_trace(rt_ctx *ctx, int32_t n_azim_2, const int64_t *n_tracks_x
     CK(cudaMemcpyAsync(&ctx->sum_len, dsum.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     unsigned long long err = 0;
     CK(cudaMemcpyAsync(&err, ctx->b_err.p, sizeof(err), cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->phase_ms[1] = toc(ctx);
+    toc(ctx, 1);
     CK(cudaStreamSynchronize(ctx->stream));
     release(dsum);
     if (err != ~0ULL) {
@@ -684,7 +700,7 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
     double launches = 0;
 
     // ---- chunk plan: cut tracks so that ~target_walkers independent walkers exist, >= chunk_segments segments each
-    tic(ctx);
+    tic(ctx, 2);
     P.n_tracks = n;
     P.trk_begin = 0;
     P.trk_end = n;
@@ -701,9 +717,9 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         k_plan_chunks<<<blocks_for(n_blocks * 32, 128), 128, 0, st>>>(n, ctx->t.len, chunk_len, (int *)ctx->b_nch.p,
                                                                      (int *)ctx->b_blk_chunks.p);
         CK((exclusive_scan<int, long long>(ctx, (const int *)ctx->b_blk_chunks.p, (long long *)ctx->b_unit_base.p, n_blocks)));
-        long long n_units = 0;
-        CK(cudaMemcpyAsync(&n_units, (long long *)ctx->b_unit_base.p + n_blocks, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&ctx->h_pin[0], (long long *)ctx->b_unit_base.p + n_blocks, sizeof(long long), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        const long long n_units = ctx->h_pin[0];
         size_t nc = (size_t)n_units * 32;
         CK(ensure(ctx->b_unit_block, sizeof(int) * (size_t)n_units));
         CK(ensure(ctx->b_ch_i, sizeof(int) * 5 * nc));
@@ -760,21 +776,23 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         launches += 3;
     }
     CK(cudaGetLastError());
-    ctx->phase_ms[2] = toc(ctx);
+    toc(ctx, 2);
     // ---- scan
-    tic(ctx);
+    tic(ctx, 3);
     long long total = 0;
     if (n > 0) {
         CK((exclusive_scan<int, long long>(ctx, (const int *)ctx->b_count.p, (long long *)ctx->b_offsets.p, n)));
         launches += 3;
-        CK(cudaMemcpyAsync(&total, (long long *)ctx->b_offsets.p + n, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&ctx->h_pin[1], (long long *)ctx->b_offsets.p + n, sizeof(long long), cudaMemcpyDeviceToHost, st));
     }
-    ctx->phase_ms[3] = toc(ctx);
+    toc(ctx, 3);
     CK(cudaStreamSynchronize(st));
+    if (n > 0) total = ctx->h_pin[1];
     ctx->total_segments = total;
 
     // ---- fill pass (possibly in uid batches over a recycled buffer)
     ctx->phase_ms[4] = 0.0;
+    ctx->pev_dirty[4] = false;
     ctx->eval_ms = 0.0;
     ctx->res_trk_begin = ctx->res_trk_end = 0;
     ctx->res_off_base = 0;
@@ -836,7 +854,7 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
             h_unit_base.resize((size_t)((n + 31) / 32) + 1);
             CK(cudaMemcpy(h_unit_base.data(), ctx->b_unit_base.p, sizeof(long long) * h_unit_base.size(), cudaMemcpyDeviceToHost));
         }
-        tic(ctx);
+        tic(ctx, 4);
         long long b = 0;
         while (b < n) {
             long long e = n;
@@ -892,9 +910,10 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
             ctx->res_off_base = P.offset_base;
             ctx->res_nseg = nseg_b;
             if (topo_count) {
-                int vf = 0;
-                CK(cudaMemcpyAsync(&vf, ctx->b_verify.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+                ctx->h_pin[2] = 0;
+                CK(cudaMemcpyAsync(&ctx->h_pin[2], ctx->b_verify.p, sizeof(int), cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
+                const int vf = (int)ctx->h_pin[2];
                 if (topo) {
                     float ems = 0.f;
                     cudaEventElapsedTime(&ems, ctx->ev2[0], ctx->ev2[1]);
@@ -902,7 +921,7 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
                 }
                 if (vf) {
                     *verify_failed = true;
-                    ctx->phase_ms[4] = toc(ctx);
+                    toc(ctx, 4);
                     return RT_OK;
                 }
             }
@@ -915,22 +934,21 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
             }
             b = e;
         }
-        ctx->phase_ms[4] = toc(ctx);
+        toc(ctx, 4);
     }
     unsigned long long bad = ~0ULL;
     if (n > 0) {
         k_first_bad<<<blocks_for(n, 256), 256, 0, st>>>((const int *)ctx->b_status.p, n, (unsigned long long *)ctx->b_bad.p);
         launches += 1;
-        CK(cudaMemcpyAsync(&bad, ctx->b_bad.p, sizeof(bad), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&ctx->h_pin[3], ctx->b_bad.p, sizeof(bad), cudaMemcpyDeviceToHost, st));
     }
-    unsigned long long hc[4] = {0, 0, 0, 0};
-    CK(cudaMemcpyAsync(hc, ctx->b_counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&ctx->h_pin[4], ctx->b_counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (n > 0) bad = (unsigned long long)ctx->h_pin[3];
+    unsigned long long hc[4];
+    for (int q = 0; q < 4; ++q) hc[q] = (unsigned long long)ctx->h_pin[4 + q];
     ctx->stats[0] += launches;
     for (int q = 0; q < 4; ++q) ctx->stats[1 + q] = (double)hc[q];
-    ctx->stats[5] = ctx->phase_ms[2];
-    ctx->stats[6] = ctx->phase_ms[4];
-    ctx->stats[7] = ctx->phase_ms[3];
     *bad_out = bad;
     return RT_OK;
 }
@@ -1101,7 +1119,7 @@ extern "C" int rt_volumes(rt_ctx *ctx, double *volumes) {
     cudaStream_t st = ctx->stream;
     int nc = ctx->m.n_cells;
     CK(ensure(ctx->b_voln, sizeof(double) * (size_t)nc));
-    tic(ctx);
+    tic(ctx, 5);
     const double *src = (const double *)ctx->b_vol.p;
     if (ctx->comm) {
         // the ONLY collective of the path: sum of per-element delta*len over the uid shards
@@ -1111,7 +1129,7 @@ extern "C" int rt_volumes(rt_ctx *ctx, double *volumes) {
     }
     k_normalise<<<blocks_for(nc, 256), 256, 0, st>>>(src, (double *)ctx->b_voln.p, nc, (double)ctx->n2);
     CK(cudaGetLastError());
-    ctx->phase_ms[5] = toc(ctx);
+    toc(ctx, 5);
     if (volumes) CK(cudaMemcpy(volumes, ctx->b_voln.p, sizeof(double) * (size_t)nc, cudaMemcpyDeviceToHost));
     return RT_OK;
 }
@@ -1174,6 +1192,11 @@ extern "C" int rt_selftest_division(rt_ctx *ctx, int64_t n_threads, uint64_t see
 
 extern "C" int rt_stats(rt_ctx *ctx, double stats[8]) {
     if (!ctx || !stats) return RT_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    collect_phase_ms(ctx);
+    ctx->stats[5] = ctx->phase_ms[2];
+    ctx->stats[6] = ctx->phase_ms[4];
+    ctx->stats[7] = ctx->phase_ms[3];
     memcpy(stats, ctx->stats, sizeof(ctx->stats));
     return RT_OK;
 }
@@ -1196,6 +1219,8 @@ extern "C" int rt_info(rt_ctx *ctx, const char *key, double *value) {
 
 extern "C" int rt_phase_ms(rt_ctx *ctx, double ms[6]) {
     if (!ctx || !ms) return RT_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    collect_phase_ms(ctx);
     memcpy(ms, ctx->phase_ms, sizeof(ctx->phase_ms));
     return RT_OK;
 }

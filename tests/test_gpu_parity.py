@@ -11,6 +11,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 import raytracing_jl_b200 as rt  # noqa: E402
+from raytracing_jl_b200 import api  # noqa: E402
 from oracle.oracle import OracleMesh, OracleTrackGenerator  # noqa: E402
 from tests.golden import runtests_goldens as G  # noqa: E402
 
@@ -323,6 +324,79 @@ def test_properties_at_scale():
     rt.segmentize_(tg, check=False)
     s2 = tg.segments
     assert chk == (float(s2["len"].sum()), int(s2["element"].astype(np.int64).sum()))
+
+
+def test_cfg4_full_size_pipelines_agree():
+    """BASELINE.json configs[3] at its FULL size (3.7 M cells, 3.5 M tracks, 7.9e9 segments, batched fill over a recycled
+    buffer).  Size-independent properties: the three independently coded pipelines produce the same stream of Segment records
+    (order- and bit-sensitive per-batch checksums computed on the device), the traced volumes add up to the mesh area, and
+    the tracks that fail the reference's own checks are the same in every pipeline.  Spot checks against the oracle: uid
+    ranges spread over the shard, plus every failing track, are compared bit for bit."""
+    import torch
+
+    from raytracing_jl_b200 import _lib as L
+
+    model, n_azim, delta = rt.synth.workload("cfg4")
+    mesh = rt.Mesh(model)
+    tg = rt.TrackGenerator(mesh, n_azim, delta, bcs=bcs_of((1, 1, 1, 1)))
+    rt.trace_(tg)
+    L.check(tg._ctx, L.lib().rt_set_segment_capacity(tg._ctx, 1_500_000_000))
+    area = rt.synth.mesh_area(model)
+    n = tg.n_total_tracks
+    ranges = [(int(u), int(u) + 40) for u in np.linspace(1, n - 40, 7)]
+    keys = ("px", "py", "qx", "qy", "len", "element")
+    results = []
+    for pipeline in (0, 1, 2):
+        tg.set_option("pipeline", pipeline)
+        chk, slices = [], {}
+
+        def on_batch(b, chk=chk, slices=slices):
+            torch.cuda.synchronize()
+            cols = {k: torch.as_tensor(getattr(b, k), device="cuda") for k in keys}
+            off = torch.as_tensor(api.DeviceColumn(b.d_offsets, n + 1, "<i8"), device="cuda")
+            row = [b.uid_begin, b.uid_end, b.n_segments]
+            step = 1 << 27
+            for lo in range(0, b.n_segments, step):
+                hi = min(b.n_segments, lo + step)
+                w = torch.arange(lo, hi, device="cuda", dtype=torch.int64) % 1021 + 1  # position-dependent weights
+                row.append(int((cols["element"][lo:hi].to(torch.int64) * w).sum()))
+                for k in keys[:5]:  # bit patterns, so that any differing bit changes the sum
+                    row.append(int((cols[k][lo:hi].view(torch.int64) & 0xFFFFFFFF).mul_(w).sum()))
+            chk.append(tuple(row))
+            for (u0, u1) in ranges:
+                if b.uid_begin <= u0 and u1 <= b.uid_end:
+                    o = off[u0 - 1:u1].cpu().numpy() - b.offset_base
+                    slices[(u0, u1)] = (o - o[0], {k: cols[k][int(o[0]):int(o[-1])].cpu().numpy() for k in keys})
+            torch.cuda.synchronize()
+
+        rt.segmentize_(tg, rtol=1e-6, check=False, on_batch=on_batch)
+        assert tg.info("verify_fallbacks") == 0
+        assert tg.n_segments > 7_000_000_000 and len(chk) >= 4
+        assert sum(r[2] for r in chk) == tg.n_segments
+        assert math.isclose(tg.volumes.sum(), area, rel_tol=1e-8)
+        results.append((tg.n_segments, chk, tg.segment_offsets.copy(), tg.segment_status.copy(), slices))
+    for other in results[1:]:
+        assert other[0] == results[0][0] and other[1] == results[0][1]
+        assert np.array_equal(other[2], results[0][2]) and np.array_equal(other[3], results[0][3])
+    # ---- the oracle on the sampled uid ranges and on every failing track
+    off, status, slices = results[0][2], results[0][3], results[0][4]
+    bad = np.nonzero(status)[0] + 1
+    assert 0 < bad.size < 1e-5 * n  # the reference's own end-of-track / length-check failures (DESIGN.md, "Error behaviour")
+    otg = OracleTrackGenerator(OracleMesh.from_mesh(mesh), n_azim, delta, bcs=(1, 1, 1, 1)).trace()
+    checked = 0
+    for (u0, u1), (o, cols) in slices.items():
+        otg.segmentize(rtol=1e-6, uid_begin=u0, uid_end=u1, fetch=True, check=False)
+        assert np.array_equal(otg.seg_offsets, o)
+        for k in keys:
+            assert np.array_equal(otg.seg[k], cols[k]), (u0, k)
+        assert np.array_equal(otg.seg_status, status[u0 - 1:u1 - 1])
+        checked += int(o[-1])
+        otg.free_segments()
+    assert len(slices) >= 5 and checked > 100_000
+    for uid in bad:
+        otg.segmentize(rtol=1e-6, uid_begin=int(uid), uid_end=int(uid) + 1, fetch=False, check=False)
+        assert otg.seg_status[0] == status[uid - 1] and otg.seg_counts[0] == off[uid] - off[uid - 1], uid
+        otg.free_segments()
 
 
 @pytest.mark.parametrize("exp_span", [0, 3, 40, 400, 520, 1022])
