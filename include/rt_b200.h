@@ -75,10 +75,17 @@ int rt_host_free(void *ptr);
  * per-edge records (general_form of every edge, src/intersection.jl:11-18) and the uniform node grid
  * that answers the exact nearest-node queries the reference asks its KD-tree (src/mesh.jl:107,123).
  * xy = x0,y0,x1,y1,... ; cell_ptrs/cell_data = get_cell_node_ids(grid) ; node_cell_ptrs/node_cell_data =
- * get_faces(topology, 0, 2) ; bb_min/bb_max = bounding_box(grid) (src/mesh.jl:53-69). Triangles only. */
+ * get_faces(topology, 0, 2) ; bb_min/bb_max = bounding_box(grid) (src/mesh.jl:53-69). Triangles only.
+ * Ingestion at scale: node_cell_ptrs/node_cell_data may both be NULL -- the vertex -> cells table is then built on the
+ * device (cells around a node in ascending cell id, Gridap's order) -- and bb_min/bb_max may both be NULL -- the bounding
+ * box is then an exact min/max reduction on the device (the reference's `min(xs...)` splat, src/mesh.jl:60-62, does not
+ * scale to million-node meshes).  rt_mesh_bbox / rt_mesh_node_cells return what was built. */
 int rt_mesh_upload(rt_ctx *ctx, int32_t n_nodes, const double *xy, int32_t n_cells, const int32_t *cell_ptrs,
                    const int32_t *cell_data, const int32_t *node_cell_ptrs, const int32_t *node_cell_data,
                    const double bb_min[2], const double bb_max[2]);
+int rt_mesh_bbox(rt_ctx *ctx, double bb_min[2], double bb_max[2]);
+/* 1-based CSR like Gridap's Table{Int32}; either pointer may be NULL. node_cell_data has 3*n_cells entries. */
+int rt_mesh_node_cells(rt_ctx *ctx, int32_t *node_cell_ptrs /* n_nodes+1 */, int32_t *node_cell_data);
 /* cell -> neighbour across edge (i, i%3+1) in the cell's stored node order, 1-based, 0 = boundary */
 int rt_mesh_neighbours(rt_ctx *ctx, int32_t *cell_nbr /* 3*n_cells */);
 

@@ -65,7 +65,9 @@ SYMBOLS = {
     "rt_version": (C.c_char_p, []),
     "rt_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     "rt_host_free": (C.c_int, [_vp]),
-    "rt_mesh_upload": (C.c_int, [_vp, C.c_int32, _f64, C.c_int32, _i32, _i32, _i32, _i32, _f64, _f64]),
+    "rt_mesh_upload": (C.c_int, [_vp, C.c_int32, _f64, C.c_int32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "rt_mesh_bbox": (C.c_int, [_vp, _f64, _f64]),
+    "rt_mesh_node_cells": (C.c_int, [_vp, _vp, _vp]),
     "rt_mesh_neighbours": (C.c_int, [_vp, _i32]),
     "rt_trace": (C.c_int, [_vp, C.c_int32, _i64, _i64, _f64, _f64, _f64, _f64, _f64, _f64, _i32, C.c_int64, C.c_int64]),
     "rt_tracks_download": (C.c_int, [_vp] + [_vp] * 13),

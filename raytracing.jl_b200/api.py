@@ -271,6 +271,20 @@ class TrackGenerator(TrackLayout):
             mesh = Mesh(model)
         else:
             raise TypeError("model must be an UnstructuredDiscreteModel")
+        AzimuthalQuadrature(n_azim, delta)  # argument errors (src/azimuthal_quad.jl:22-25) come before any device work
+        self.mesh = mesh
+        self._pinned, self._pinned_mesh, self._ctx = {}, None, None
+        # device context + mesh upload (Mesh(model), src/mesh.jl:24-31) -- before the layout: with device-side ingestion the
+        # bounding box the layout needs comes back from the device
+        L = _lib.lib()
+        h = C.c_void_p()
+        rc = L.rt_create(C.byref(h), int(device))
+        if rc:
+            raise _lib.RTError(rc, f"rt_create(device={device}) failed: no usable CUDA device (there is no CPU fallback)")
+        self._ctx = h
+        self._traced = self._segmented = False
+        self._track_data = self._segments = self._offsets = None
+        self.upload_mesh()
         super().__init__(mesh, n_azim, delta)
         self.bcs = bcs if bcs is not None else BoundaryConditions()
         self.tiny_step = float(tiny_step)
@@ -286,24 +300,22 @@ class TrackGenerator(TrackLayout):
         self._segments = None
         self._offsets = None
         self._resident_base = 0
-        self._pinned = {}
         self.n_segments = 0
-        # device context + mesh upload (Mesh(model), src/mesh.jl:24-31)
-        L = _lib.lib()
-        h = C.c_void_p()
-        rc = L.rt_create(C.byref(h), int(device))
-        if rc:
-            raise _lib.RTError(rc, f"rt_create(device={device}) failed: no usable CUDA device (there is no CPU fallback)")
-        self._ctx = h
-        self.upload_mesh()
+
+    def _mesh_arrays(self):
+        """The arrays rt_mesh_upload reads: xy, cell ptrs/data and -- unless the mesh leaves them to the device -- the
+        vertex->cells ptrs/data."""
+        mesh, m = self.mesh, self.mesh.model
+        a = [m.node_coordinates.reshape(-1), mesh.cell_nodes[0], mesh.cell_nodes[1]]
+        if not mesh.device_ingest:
+            a += [mesh.node_cells[0], mesh.node_cells[1]]
+        return a
 
     def pin_mesh(self):
-        """Keep the five flattened mesh arrays in page-locked host memory, so that upload_mesh() is one asynchronous DMA per
+        """Keep the flattened mesh arrays in page-locked host memory, so that upload_mesh() is one asynchronous DMA per
         array at full PCIe rate (a Julia caller would register its Gridap arrays with cudaHostRegister instead)."""
-        mesh, m = self.mesh, self.mesh.model
-        src = [m.node_coordinates.reshape(-1), mesh.cell_nodes[0], mesh.cell_nodes[1], mesh.node_cells[0], mesh.node_cells[1]]
         self._pinned_mesh = []
-        for a in src:
+        for a in self._mesh_arrays():
             buf = _lib.PinnedArray(a.shape, a.dtype)
             buf.array[...] = a
             self._pinned_mesh.append(buf)
@@ -311,19 +323,29 @@ class TrackGenerator(TrackLayout):
     def upload_mesh(self):
         """Host -> device copy of the flattened mesh + device-side preparation (rt_mesh_upload)."""
         mesh, m = self.mesh, self.mesh.model
-        if getattr(self, "_pinned_mesh", None):
-            xy, cp, cd, np_, nd = (b.array for b in self._pinned_mesh)
-        else:
-            xy, cp, cd, np_, nd = (m.node_coordinates.reshape(-1), mesh.cell_nodes[0], mesh.cell_nodes[1], mesh.node_cells[0],
-                                   mesh.node_cells[1])
-        _lib.check(self._ctx, _lib.lib().rt_mesh_upload(self._ctx, m.num_nodes, xy, m.num_cells, cp, cd, np_, nd, mesh.bb_min,
-                                                        mesh.bb_max))
+        arrs = [b.array for b in self._pinned_mesh] if self._pinned_mesh else self._mesh_arrays()
+        xy, cp, cd = arrs[:3]
+        np_, nd = (arrs[3], arrs[4]) if len(arrs) == 5 else (None, None)
+        L = _lib.lib()
+        _lib.check(self._ctx, L.rt_mesh_upload(self._ctx, m.num_nodes, xy, m.num_cells, cp, cd, _lib.ptr(np_), _lib.ptr(nd),
+                                               _lib.ptr(mesh.bb_min), _lib.ptr(mesh.bb_max)))
+        if mesh.bb_min is None:  # reduced on the device (src/mesh.jl:53-69)
+            lo, hi = np.zeros(2), np.zeros(2)
+            _lib.check(self._ctx, L.rt_mesh_bbox(self._ctx, lo, hi))
+            mesh.bb_min, mesh.bb_max = lo, hi
         self._traced = self._segmented = False
         self._track_data = self._segments = self._offsets = None
 
+    def device_node_cells(self):
+        """The vertex->cells table as the device holds it (1-based CSR like Gridap's Table)."""
+        m = self.mesh.model
+        ptrs, data = np.zeros(m.num_nodes + 1, np.int32), np.zeros(3 * m.num_cells, np.int32)
+        _lib.check(self._ctx, _lib.lib().rt_mesh_node_cells(self._ctx, _lib.ptr(ptrs), _lib.ptr(data)))
+        return ptrs, data
+
     def mesh_h2d_bytes(self) -> int:
         mesh, m = self.mesh, self.mesh.model
-        return int(m.node_coordinates.nbytes + sum(a.nbytes for a in mesh.cell_nodes) + sum(a.nbytes for a in mesh.node_cells))
+        return int(sum(a.nbytes for a in self._mesh_arrays()))
 
     def set_option(self, name: str, value: float):
         _lib.check(self._ctx, _lib.lib().rt_set_option(self._ctx, name.encode(), float(value)))

@@ -60,6 +60,75 @@ __global__ void k_to_zero_based(const int32_t *in, int *out, int64_t n) {
     if (i < n) out[i] = in[i] - 1;
 }
 
+// ---- device-side ingestion: the tables the reference takes from Gridap / computes with a splat ----------------
+// bounding_box(grid) (src/mesh.jl:53-69) = min / max over all node coordinates: an exact, order-independent reduction.
+__device__ __forceinline__ void atomic_min_double_any(double *addr, double v) {
+    unsigned long long *a = (unsigned long long *)addr, old = *a, assumed;
+    do {
+        assumed = old;
+        if (!(v < __longlong_as_double((long long)assumed))) break;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+    } while (old != assumed);
+}
+__device__ __forceinline__ void atomic_max_double_any(double *addr, double v) {
+    unsigned long long *a = (unsigned long long *)addr, old = *a, assumed;
+    do {
+        assumed = old;
+        if (!(v > __longlong_as_double((long long)assumed))) break;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+    } while (old != assumed);
+}
+// bb = {min x, min y, max x, max y}, initialised to {+inf, +inf, -inf, -inf}
+__global__ void k_bbox(const double2 *xy, int n_nodes, double *bb) {
+    double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_nodes; i += gridDim.x * blockDim.x) {
+        const double2 p = xy[i];
+        mnx = fmin(mnx, p.x);
+        mny = fmin(mny, p.y);
+        mxx = fmax(mxx, p.x);
+        mxy = fmax(mxy, p.y);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mnx = fmin(mnx, __shfl_down_sync(0xffffffffu, mnx, o));
+        mny = fmin(mny, __shfl_down_sync(0xffffffffu, mny, o));
+        mxx = fmax(mxx, __shfl_down_sync(0xffffffffu, mxx, o));
+        mxy = fmax(mxy, __shfl_down_sync(0xffffffffu, mxy, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomic_min_double_any(&bb[0], mnx);
+        atomic_min_double_any(&bb[1], mny);
+        atomic_max_double_any(&bb[2], mxx);
+        atomic_max_double_any(&bb[3], mxy);
+    }
+}
+
+// vertex -> cells table = get_faces(get_grid_topology(model), 0, 2) (src/mesh.jl:27): cells around each node in ASCENDING cell
+// id (the order find_element scans them in, src/mesh.jl:110).  count -> scan -> fill (atomic cursor) -> per-node sort.
+__global__ void k_nc_count(int n_cells, const int *cell_nodes, int *deg) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < 3 * (int64_t)n_cells) atomicAdd(&deg[cell_nodes[t]], 1);
+}
+__global__ void k_nc_fill(int n_cells, const int *cell_nodes, const int *ptrs, int *cursor, int *data) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= 3 * (int64_t)n_cells) return;
+    const int node = cell_nodes[t];
+    data[ptrs[node] + atomicAdd(&cursor[node], 1)] = (int)(t / 3);
+}
+__global__ void k_nc_sort(int n_nodes, const int *ptrs, int *data) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const int b = ptrs[i], e = ptrs[i + 1];
+    for (int q = b + 1; q < e; ++q) {  // insertion sort: the valence of a mesh node is small
+        const int v = data[q];
+        int r = q - 1;
+        while (r >= b && data[r] > v) {
+            data[r + 1] = data[r];
+            --r;
+        }
+        data[r + 1] = v;
+    }
+}
+
 // one thread per (cell, edge): the neighbour is the other cell around node a that also contains node b
 __global__ void k_neighbours(int n_cells, const int *cell_nodes, const int *nc_ptrs, const int *nc_data, int *nbr) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;

@@ -244,15 +244,17 @@ extern "C" int rt_mesh_upload(rt_ctx *ctx, int32_t n_nodes, const double *xy, in
                               const int32_t *cell_data, const int32_t *node_cell_ptrs, const int32_t *node_cell_data,
                               const double bb_min[2], const double bb_max[2]) {
     if (!ctx) return RT_ERR_ARG;
-    if (n_nodes < 3 || n_cells < 1 || !xy || !cell_ptrs || !cell_data || !node_cell_ptrs || !node_cell_data)
+    if (n_nodes < 3 || n_cells < 1 || !xy || !cell_ptrs || !cell_data || (!node_cell_ptrs != !node_cell_data) || (!bb_min != !bb_max))
         return fail(ctx, RT_ERR_ARG, "rt_mesh_upload: null or empty mesh arrays");
+    const bool dev_nc = node_cell_ptrs == nullptr;  // build the vertex -> cells table on the device
+    const bool dev_bb = bb_min == nullptr;          // reduce the bounding box on the device
     for (int32_t c = 0; c < n_cells; ++c)
         if (cell_ptrs[c + 1] - cell_ptrs[c] != 3)
             return fail(ctx, RT_ERR_ARG, "rt_mesh_upload: cell %d is not a triangle (reference src/mesh.jl:149-150)", c + 1);
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     tic(ctx, 0);
-    size_t n_nc = (size_t)(node_cell_ptrs[n_nodes] - 1);
+    size_t n_nc = dev_nc ? (size_t)3 * n_cells : (size_t)(node_cell_ptrs[n_nodes] - 1);
     CK(ensure(ctx->b_xy, sizeof(double2) * (size_t)n_nodes));
     CK(ensure(ctx->b_cell_nodes, sizeof(int) * 3 * (size_t)n_cells));
     CK(ensure(ctx->b_nc_ptrs, sizeof(int) * ((size_t)n_nodes + 1)));
@@ -265,19 +267,49 @@ extern "C" int rt_mesh_upload(rt_ctx *ctx, int32_t n_nodes, const double *xy, in
     CK(ensure(ctx->b_sc, sizeof(MeshScalars)));
     // stage the 1-based tables through a (persistent) scratch buffer and convert on the device; no host synchronisation here:
     // the three tables use disjoint scratch regions
-    const size_t tab_n[3] = {(size_t)3 * n_cells, (size_t)n_nodes + 1, n_nc};
+    const size_t tab_n[3] = {(size_t)3 * n_cells, dev_nc ? 0 : (size_t)n_nodes + 1, dev_nc ? 0 : n_nc};
     CK(ensure(ctx->b_scratch, sizeof(int32_t) * (tab_n[0] + tab_n[1] + tab_n[2])));
     CK(cudaMemcpyAsync(ctx->b_xy.p, xy, sizeof(double) * 2 * (size_t)n_nodes, cudaMemcpyHostToDevice, st));
     const int32_t *tab_src[3] = {cell_data, node_cell_ptrs, node_cell_data};
     void *tab_dst[3] = {ctx->b_cell_nodes.p, ctx->b_nc_ptrs.p, ctx->b_nc_data.p};
     size_t tab_off = 0;
     for (int q = 0; q < 3; ++q) {
+        if (tab_n[q] == 0) continue;
         int32_t *stage = (int32_t *)ctx->b_scratch.p + tab_off;
         CK(cudaMemcpyAsync(stage, tab_src[q], sizeof(int32_t) * tab_n[q], cudaMemcpyHostToDevice, st));
         k_to_zero_based<<<blocks_for((long long)tab_n[q], 256), 256, 0, st>>>(stage, (int *)tab_dst[q], (long long)tab_n[q]);
         tab_off += tab_n[q];
     }
 
+    if (dev_nc) {  // count -> scan -> fill -> sort (ascending cell id around every node, src/mesh.jl:27)
+        DevBuf deg, cur;
+        CK(ensure(deg, sizeof(int) * (size_t)n_nodes));
+        CK(ensure(cur, sizeof(int) * (size_t)n_nodes));
+        CK(cudaMemsetAsync(deg.p, 0, sizeof(int) * (size_t)n_nodes, st));
+        CK(cudaMemsetAsync(cur.p, 0, sizeof(int) * (size_t)n_nodes, st));
+        k_nc_count<<<blocks_for(3LL * n_cells, 256), 256, 0, st>>>(n_cells, (const int *)ctx->b_cell_nodes.p, (int *)deg.p);
+        CK((exclusive_scan<int, int>(ctx, (const int *)deg.p, (int *)ctx->b_nc_ptrs.p, (long long)n_nodes)));
+        k_nc_fill<<<blocks_for(3LL * n_cells, 256), 256, 0, st>>>(n_cells, (const int *)ctx->b_cell_nodes.p, (const int *)ctx->b_nc_ptrs.p,
+                                                                   (int *)cur.p, (int *)ctx->b_nc_data.p);
+        k_nc_sort<<<blocks_for(n_nodes, 256), 256, 0, st>>>(n_nodes, (const int *)ctx->b_nc_ptrs.p, (int *)ctx->b_nc_data.p);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(st));
+        release(deg);
+        release(cur);
+    }
+    double bbv[4];
+    if (dev_bb) {
+        DevBuf dbb;
+        CK(ensure(dbb, sizeof(double) * 4));
+        const double init[4] = {INFINITY, INFINITY, -INFINITY, -INFINITY};
+        CK(cudaMemcpyAsync(dbb.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        k_bbox<<<std::min(1024u, blocks_for(n_nodes, 256)), 256, 0, st>>>((const double2 *)ctx->b_xy.p, n_nodes, (double *)dbb.p);
+        CK(cudaMemcpyAsync(bbv, dbb.p, sizeof(bbv), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        release(dbb);
+        bb_min = bbv;
+        bb_max = bbv + 2;
+    }
     DevMesh &m = ctx->m;
     m.n_nodes = n_nodes;
     m.n_cells = n_cells;
@@ -344,6 +376,31 @@ extern "C" int rt_mesh_upload(rt_ctx *ctx, int32_t n_nodes, const double *xy, in
     ctx->has_mesh = true;
     ctx->traced = false;
     ctx->segmented = false;
+    return RT_OK;
+}
+
+extern "C" int rt_mesh_bbox(rt_ctx *ctx, double bb_min[2], double bb_max[2]) {
+    if (!ctx || !ctx->has_mesh || !bb_min || !bb_max) return fail(ctx, RT_ERR_ARG, "rt_mesh_bbox: no mesh");
+    for (int q = 0; q < 2; ++q) {
+        bb_min[q] = ctx->m.bbmin[q];
+        bb_max[q] = ctx->m.bbmax[q];
+    }
+    return RT_OK;
+}
+
+extern "C" int rt_mesh_node_cells(rt_ctx *ctx, int32_t *node_cell_ptrs, int32_t *node_cell_data) {
+    if (!ctx || !ctx->has_mesh) return fail(ctx, RT_ERR_ARG, "rt_mesh_node_cells: no mesh");
+    CK(cudaSetDevice(ctx->device));
+    const size_t nn = (size_t)ctx->m.n_nodes;
+    std::vector<int> ptrs(nn + 1);
+    CK(cudaMemcpy(ptrs.data(), ctx->b_nc_ptrs.p, sizeof(int) * (nn + 1), cudaMemcpyDeviceToHost));
+    if (node_cell_ptrs)
+        for (size_t i = 0; i <= nn; ++i) node_cell_ptrs[i] = ptrs[i] + 1;  // 1-based like Gridap's Table
+    if (node_cell_data) {
+        const size_t n = (size_t)ptrs[nn];
+        CK(cudaMemcpy(node_cell_data, ctx->b_nc_data.p, sizeof(int) * n, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; ++i) node_cell_data[i] += 1;
+    }
     return RT_OK;
 }
 

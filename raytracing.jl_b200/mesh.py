@@ -140,14 +140,27 @@ class Mesh:
     ``cell_nodes`` (both as (ptrs, data) 1-based CSR pairs), ``bb_min``, ``bb_max``.  The KD-tree of the
     reference is replaced by a uniform node grid built on the device at upload time."""
 
-    def __init__(self, model: UnstructuredDiscreteModel):
+    def __init__(self, model: UnstructuredDiscreteModel, device_ingest: bool = False):
+        """``device_ingest=True`` leaves the vertex->cells table and the bounding box to the device (``rt_mesh_upload`` with
+        NULL tables): nothing of size O(mesh) is computed on the host.  ``bb_min``/``bb_max`` are then filled in by the first
+        ``TrackGenerator`` built on this mesh, and ``node_cells`` is computed on first use (the oracle needs it)."""
         self.model = model
         self.cell_nodes = (model.cell_ptrs, model.cell_data)
-        self.node_cells = vertex_to_cells(model.num_nodes, model.cell_ptrs, model.cell_data)
-        xy = model.node_coordinates
-        # src/mesh.jl:53-69: min / max over all node coordinates
-        self.bb_min = np.array([xy[:, 0].min(), xy[:, 1].min()], dtype=np.float64)
-        self.bb_max = np.array([xy[:, 0].max(), xy[:, 1].max()], dtype=np.float64)
+        self.device_ingest = bool(device_ingest)
+        self._node_cells = None
+        self.bb_min = self.bb_max = None
+        if not device_ingest:
+            self._node_cells = vertex_to_cells(model.num_nodes, model.cell_ptrs, model.cell_data)
+            xy = model.node_coordinates
+            # src/mesh.jl:53-69: min / max over all node coordinates
+            self.bb_min = np.array([xy[:, 0].min(), xy[:, 1].min()], dtype=np.float64)
+            self.bb_max = np.array([xy[:, 0].max(), xy[:, 1].max()], dtype=np.float64)
+
+    @property
+    def node_cells(self):
+        if self._node_cells is None:
+            self._node_cells = vertex_to_cells(self.model.num_nodes, self.model.cell_ptrs, self.model.cell_data)
+        return self._node_cells
 
     @property
     def width(self) -> float:  # src/mesh.jl:76

@@ -269,6 +269,29 @@ def test_neighbour_table(pincell_model):
             assert nb[c, k] == (cs[0] + 1 if cs else 0)
 
 
+@pytest.mark.parametrize("which", ["pincell", "lattice", "offset"])
+def test_device_side_ingestion(pincell_model, which):
+    """vertex->cells table and bounding box built on the device (rt_mesh_upload with NULL tables) equal the host
+    ones (Gridap order: ascending cell id around every node; exact min/max), and the whole path gives the same bits."""
+    if which == "pincell":
+        model, n_azim, delta = pincell_model, 8, 0.02
+    elif which == "lattice":
+        model, n_azim, delta = rt.synth.pin_lattice_mesh(3, 1.26, 0.4096, 0.0655, 0.09, 5), 16, 0.03
+    else:
+        model, n_azim, delta = rt.synth.jittered_triangle_mesh(23, 17, 2.5, 1.25, 0.3, 11, x0=-3.25, y0=7.5), 8, 0.04
+    host = rt.Mesh(model)
+    dev = rt.Mesh(model, device_ingest=True)
+    assert dev.bb_min is None and dev._node_cells is None
+    tg = rt.TrackGenerator(dev, n_azim, delta, bcs=bcs_of((1, 1, 1, 1)))
+    assert np.array_equal(dev.bb_min, host.bb_min) and np.array_equal(dev.bb_max, host.bb_max)
+    ptrs, data = tg.device_node_cells()
+    assert np.array_equal(ptrs, host.node_cells[0]) and np.array_equal(data, host.node_cells[1])
+    rt.segmentize_(rt.trace_(tg))
+    otg = OracleTrackGenerator(OracleMesh.from_mesh(host), n_azim, delta, bcs=(1, 1, 1, 1)).trace().segmentize()
+    assert_segments_equal(otg, tg)
+    assert_volumes_close(otg, tg)
+
+
 def test_shard_planner_matches_device(pincell_model):
     from raytracing_jl_b200 import _lib
     from raytracing_jl_b200.api import _angle_tables
