@@ -145,6 +145,38 @@ int rt_segments_download(rt_ctx *ctx, double *px, double *py, double *qx, double
 /* device-resident view of the resident batch for on-GPU consumers (transport sweeps) */
 int rt_segments_device(rt_ctx *ctx, rt_batch *view);
 
+/* ---- what a transport sweep consumes besides the Segment records, kept on the device -------------
+ * Device-resident view of the shard's Track records (src/track.jl:42-57): the cyclic links next_track_fwd/bwd
+ * (src/trackgenerator.jl:282-348, as 1-based GLOBAL uids), link directions and boundary conditions are what the sweep
+ * follows from one track to the next; d_azim indexes the per-angle tables of rt_quad_view (0-based). */
+typedef struct rt_track_view {
+    int64_t uid_begin, n_tracks;                      /* track i of the arrays has uid = uid_begin + i */
+    const double *d_px, *d_py, *d_qx, *d_qy, *d_len;  /* track.p, track.q, track.l */
+    const double *d_a, *d_b, *d_c;                    /* track.ABC */
+    const int32_t *d_azim;                            /* azim_idx - 1 */
+    const int64_t *d_track_idx, *d_next_fwd, *d_next_bwd;
+    const int8_t *d_bc_fwd, *d_bc_bwd, *d_dir_fwd, *d_dir_bwd; /* RT_VACUUM.. / RT_FORWARD.. */
+    void *stream;
+} rt_track_view;
+int rt_tracks_device(rt_ctx *ctx, rt_track_view *view);
+
+/* Per-angle tables on the device: phi, sin, cos (as passed to rt_trace), delta_eff (as passed to rt_segmentize, NULL before),
+ * and the azimuthal weights omega of init_weights! (src/azimuthal_quad.jl:35-53), computed on the device from phi with the
+ * reference's formula; omega_host (n_azim_2 doubles) receives a copy when not NULL. */
+typedef struct rt_quad_view {
+    int32_t n_azim_2;
+    const double *d_phi, *d_sin, *d_cos, *d_delta_eff, *d_omega;
+} rt_quad_view;
+int rt_quadrature_device(rt_ctx *ctx, rt_quad_view *view, double *omega_host);
+
+/* tau[s][g] = sigma_t[element(s)][g] * len(s) for every segment of the resident batch: the `tau::Vector{T}` of each Segment
+ * (src/segment.jl:27), which the reference leaves empty for the transport code.  sigma_t: HOST array, n_cells x n_groups
+ * (element-major).  layout 0: tau[s*n_groups + g] (the reference's per-segment vectors, concatenated); layout 1:
+ * tau[g*n_segments + s].  *d_tau receives the device buffer (owned by the context, valid until the next call);
+ * tau_host, when not NULL, receives a copy. */
+int rt_optical_lengths(rt_ctx *ctx, int32_t n_groups, const double *sigma_t, int32_t layout, const double **d_tau,
+                       double *tau_host);
+
 /* ---- volumes: replaces the tail of fill_volumes (src/trackgenerator.jl:378-386) -----------------------
  * volumes[e] = (sum over this context's segments of delta_eff[azim]*len) / n_azim_2, after an NCCL
  * all-reduce across the communicator set up with rt_comm_init (skipped when there is none). */
@@ -160,7 +192,8 @@ int rt_comm_init(rt_ctx *ctx, int32_t n_ranks, int32_t rank, const char id[128])
  * stats[0..7] of the last rt_segmentize: kernel launches, fast transitions, slow (literal) iterations,
  * nearest-node queries, knn queries, count-pass ms, fill-pass ms, scan+volumes ms. */
 int rt_stats(rt_ctx *ctx, double stats[8]);
-/* named scalars of the last rt_segmentize: "verify_fallbacks", "eval_ms" (k_eval alone), "n_units", "segment_capacity" */
+/* named scalars: "verify_fallbacks", "eval_ms" (stage 2 of the two-stage fill), "n_units", "segment_capacity" of the last
+ * rt_segmentize; "tau_ms" (k_tau alone) of the last rt_optical_lengths */
 int rt_info(rt_ctx *ctx, const char *key, double *value);
 /* CUDA-event time (ms) of the last call's device work, by phase: 0 upload+prep, 1 trace, 2 count,
  * 3 scan, 4 fill, 5 volumes(+allreduce) */

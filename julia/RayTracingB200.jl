@@ -138,3 +138,50 @@ function b200_segmentize!(t::TrackGenerator{T}; k::Int=5, rtol::Real=Base.rtolde
     _b200_check(ctx, ccall((:rt_volumes, LIBRT_B200), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx, volumes))
     return t
 end
+
+# ---- what a transport sweep consumes, kept on the device (include/rt_b200.h: rt_tracks_device, rt_quadrature_device,
+# ---- rt_optical_lengths) -------------------------------------------------------------------------------------------
+
+"""
+    b200_optical_lengths!(t::TrackGenerator, Σt::Matrix{Float64}) -> Matrix{Float64}
+
+`τ[g, s] = Σt[g, element(s)] * ℓ(s)` for every segment, evaluated on the device (`Σt` is n_groups × n_cells, so its memory is
+the element-major n_cells × n_groups array the ABI asks for) and copied into each `segment.τ` (src/segment.jl:27), which the
+reference leaves empty.  The device buffer stays resident for an on-GPU sweep.
+"""
+function b200_optical_lengths!(t::TrackGenerator{T}, Σt::Matrix{Float64}) where {T}
+    ctx = _b200_context(t)
+    G = size(Σt, 1)
+    S = sum(length(track.segments) for track in t.tracks_by_uid)
+    τ = Matrix{Float64}(undef, G, S)                          # layout 0: per-segment vectors, concatenated
+    dτ = Ref{Ptr{Float64}}(C_NULL)
+    _b200_check(ctx, ccall((:rt_optical_lengths, LIBRT_B200), Cint,
+        (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Ptr{Ptr{Float64}}, Ptr{Float64}), ctx, Int32(G), Σt, Int32(0), dτ, τ))
+    s = 0
+    for track in t.tracks_by_uid, segment in track.segments
+        s += 1
+        resize!(segment.τ, G); copyto!(segment.τ, view(τ, :, s))
+    end
+    return τ
+end
+
+"""
+    b200_mesh_upload_device_ingest(ctx, model)
+
+Mesh ingestion at scale: only node coordinates and the cell→node table cross the ABI; the vertex→cells table
+(`get_faces(topology, 0, 2)`, src/mesh.jl:27) and the bounding box (src/mesh.jl:53-69, whose `min(xs...)` splat does not
+scale) are built on the device.  Returns `(bb_min, bb_max)`.
+"""
+function b200_mesh_upload_device_ingest(ctx::Ptr{Cvoid}, model)
+    grid = get_grid(model)
+    coords = get_node_coordinates(grid)
+    cn = get_cell_node_ids(grid)
+    rc = ccall((:rt_mesh_upload, LIBRT_B200), Cint,
+        (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
+        ctx, Int32(length(coords)), reinterpret(Float64, coords), Int32(length(cn)), Vector{Int32}(cn.ptrs),
+        Vector{Int32}(cn.data), C_NULL, C_NULL, C_NULL, C_NULL)
+    _b200_check(ctx, rc)
+    lo = zeros(2); hi = zeros(2)
+    _b200_check(ctx, ccall((:rt_mesh_bbox, LIBRT_B200), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), ctx, lo, hi))
+    return Point2D(lo[1], lo[2]), Point2D(hi[1], hi[2])
+end

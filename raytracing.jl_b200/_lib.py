@@ -15,7 +15,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SO_PATH = os.environ.get("RT_B200_LIB") or os.path.join(_PKG, "librt_b200.so")  # RT_B200_LIB: an alternative build
 _CSRC = os.path.join(_PKG, "csrc")
-_SOURCES = ["rt_b200.cu", "geom.cuh", "mesh_dev.cuh", "walk.cuh", "topo.cuh", "eval.cuh", "trace.cuh", "scan.cuh"]
+_SOURCES = ["rt_b200.cu", "geom.cuh", "mesh_dev.cuh", "walk.cuh", "topo.cuh", "eval.cuh", "sweep.cuh", "trace.cuh", "scan.cuh"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -57,6 +57,16 @@ class rt_batch(C.Structure):
 
 BATCH_CB = C.CFUNCTYPE(C.c_int, C.POINTER(rt_batch), _vp)
 
+
+class rt_track_view(C.Structure):
+    _fields_ = [("uid_begin", C.c_int64), ("n_tracks", C.c_int64)] + [(n, _vp) for n in (
+        "d_px", "d_py", "d_qx", "d_qy", "d_len", "d_a", "d_b", "d_c", "d_azim", "d_track_idx", "d_next_fwd", "d_next_bwd",
+        "d_bc_fwd", "d_bc_bwd", "d_dir_fwd", "d_dir_bwd", "stream")]
+
+
+class rt_quad_view(C.Structure):
+    _fields_ = [("n_azim_2", C.c_int32)] + [(n, _vp) for n in ("d_phi", "d_sin", "d_cos", "d_delta_eff", "d_omega")]
+
 # name -> (restype, argtypes); every symbol include/rt_b200.h declares
 SYMBOLS = {
     "rt_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
@@ -79,6 +89,9 @@ SYMBOLS = {
     "rt_segments_download": (C.c_int, [_vp] + [_vp] * 6),
     "rt_segments_device": (C.c_int, [_vp, C.POINTER(rt_batch)]),
     "rt_volumes": (C.c_int, [_vp, _vp]),
+    "rt_tracks_device": (C.c_int, [_vp, C.POINTER(rt_track_view)]),
+    "rt_quadrature_device": (C.c_int, [_vp, C.POINTER(rt_quad_view), _vp]),
+    "rt_optical_lengths": (C.c_int, [_vp, C.c_int32, _f64, C.c_int32, C.POINTER(_vp), _vp]),
     "rt_comm_unique_id": (C.c_int, [_vp, C.c_char_p]),
     "rt_comm_init": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_char_p]),
     "rt_stats": (C.c_int, [_vp, _f64]),

@@ -418,6 +418,46 @@ class TrackGenerator(TrackLayout):
         self._segments = out
         return out
 
+    # ---- sweep-facing device views ----------------------------------------------------
+    def track_view(self):
+        """Device-resident Track records of this shard (``rt_tracks_device``) as ``DeviceColumn``s: p, q, len, ABC, azim,
+        next-track uids, boundary conditions and link directions -- what a transport sweep follows between tracks."""
+        v = _lib.rt_track_view()
+        _lib.check(self._ctx, _lib.lib().rt_tracks_device(self._ctx, C.byref(v)))
+        n = int(v.n_tracks)
+        kinds = {"d_azim": "<i4", "d_track_idx": "<i8", "d_next_fwd": "<i8", "d_next_bwd": "<i8", "d_bc_fwd": "|i1",
+                 "d_bc_bwd": "|i1", "d_dir_fwd": "|i1", "d_dir_bwd": "|i1"}
+        out = {"uid_begin": int(v.uid_begin), "n_tracks": n}
+        for name, _ in v._fields_[2:-1]:
+            out[name[2:]] = DeviceColumn(getattr(v, name), n, kinds.get(name, "<f8"))
+        return out
+
+    def quadrature_device(self):
+        """(omega, view): the azimuthal weights of init_weights! computed on the device, and DeviceColumns of the per-angle
+        tables phi / sin / cos / delta_eff / omega."""
+        v = _lib.rt_quad_view()
+        n2 = nazim2(self.azimuthal_quadrature)
+        omega = np.zeros(n2)
+        _lib.check(self._ctx, _lib.lib().rt_quadrature_device(self._ctx, C.byref(v), _lib.ptr(omega)))
+        view = {k[2:]: DeviceColumn(getattr(v, k), n2, "<f8") for k in ("d_phi", "d_sin", "d_cos", "d_delta_eff", "d_omega")
+                if getattr(v, k)}
+        return omega, view
+
+    def optical_lengths(self, sigma_t, layout: int = 0, fetch: bool = True):
+        """tau[s][g] = sigma_t[element(s)][g] * len(s) on the device for the resident segments (Segment.tau, src/segment.jl:27).
+        ``sigma_t``: (n_cells, n_groups).  Returns (numpy copy or None, DeviceColumn)."""
+        sig = np.ascontiguousarray(sigma_t, dtype=np.float64)
+        if sig.ndim != 2 or sig.shape[0] != self.mesh.num_cells:
+            raise ValueError("sigma_t must have shape (n_cells, n_groups)")
+        G = sig.shape[1]
+        view = _lib.rt_batch()
+        _lib.check(self._ctx, _lib.lib().rt_segments_device(self._ctx, C.byref(view)))
+        n = int(view.n_segments)
+        host = np.zeros((n, G) if layout == 0 else (G, n)) if fetch else None
+        d = C.c_void_p()
+        _lib.check(self._ctx, _lib.lib().rt_optical_lengths(self._ctx, G, sig.reshape(-1), int(layout), C.byref(d), _lib.ptr(host)))
+        return host, DeviceColumn(d.value, n * G, "<f8")
+
     def phase_ms(self):
         ms = np.zeros(6)
         _lib.lib().rt_phase_ms(self._ctx, ms)

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "scan.cuh"
+#include "sweep.cuh"
 #include "eval.cuh"
 #include "topo.cuh"
 #include "trace.cuh"
@@ -77,6 +78,7 @@ struct rt_ctx {
     DevBuf b_nch, b_blk_chunks, b_unit_base, b_unit_block, b_ch_i, b_ch_d;  // chunk plan (walk.cuh ChunkPlan)
     DevBuf b_order, b_okeys, b_ohist;  // spatial execution order of the units
     DevBuf b_evalblk, b_trkrec;
+    DevBuf b_omega, b_sigma, b_tau;  // sweep-facing exports (sweep.cuh)
     long long *h_pin = nullptr;  // page-locked scratch for the small device->host read-backs of rt_segmentize (16 words)
     DevBuf b_scratch, b_gcounts, b_gcursor;  // rt_mesh_upload staging (kept between uploads)
     DevBuf b_rec, b_verify, b_tsum;    // two-stage pipeline: per-segment records, verification flag, per-track length sums
@@ -84,7 +86,7 @@ struct rt_ctx {
                                        // 2: two-stage (sign-test walks + one thread per segment); 0 and 2 fall back to 1
     int verify_fallbacks = 0;
     int opt_debug_verify_fail = 0;     // test hook: make the verification of the two-stage pipeline fail
-    double eval_ms = 0.0;
+    double eval_ms = 0.0, tau_ms = 0.0;
     cudaEvent_t ev2[2] = {nullptr, nullptr};
     int opt_order_grid = 16;           // G x G tiles (0: identity order)
     int n_sm = 148;
@@ -204,7 +206,8 @@ extern "C" void rt_destroy(rt_ctx *ctx) {
                      &ctx->b_twin,    &ctx->b_he,         &ctx->b_node_reach,
                      &ctx->b_nch,     &ctx->b_blk_chunks, &ctx->b_unit_base, &ctx->b_unit_block, &ctx->b_ch_i, &ctx->b_ch_d,
                      &ctx->b_order,   &ctx->b_okeys,      &ctx->b_ohist,     &ctx->b_rec,     &ctx->b_verify,    &ctx->b_tsum,      &ctx->b_evalblk,   &ctx->b_trkrec,
-                     &ctx->b_scratch, &ctx->b_gcounts,   &ctx->b_gcursor};
+                     &ctx->b_scratch, &ctx->b_gcounts,   &ctx->b_gcursor,
+                     &ctx->b_omega,   &ctx->b_sigma,     &ctx->b_tau};
     for (DevBuf *b : all) release(*b);
     for (int ph = 0; ph < 6; ++ph)
         for (int q = 0; q < 2; ++q)
@@ -1125,6 +1128,82 @@ extern "C" int rt_segments_device(rt_ctx *ctx, rt_batch *view) {
 }
 
 // ------------------------------------------------------------------------------------------------------
+// sweep-facing device views
+// ------------------------------------------------------------------------------------------------------
+extern "C" int rt_tracks_device(rt_ctx *ctx, rt_track_view *v) {
+    if (!ctx || !v) return RT_ERR_ARG;
+    if (!ctx->traced) return fail(ctx, RT_ERR_NOT_TRACED, "rt_tracks_device: call rt_trace first");
+    const TrackSoA &t = ctx->t;
+    v->uid_begin = ctx->uid_begin;
+    v->n_tracks = ctx->n_shard;
+    v->d_px = t.px;
+    v->d_py = t.py;
+    v->d_qx = t.qx;
+    v->d_qy = t.qy;
+    v->d_len = t.len;
+    v->d_a = t.a;
+    v->d_b = t.b;
+    v->d_c = t.c;
+    v->d_azim = t.azim;
+    v->d_track_idx = (const int64_t *)t.track_idx;
+    v->d_next_fwd = (const int64_t *)t.next_fwd;
+    v->d_next_bwd = (const int64_t *)t.next_bwd;
+    v->d_bc_fwd = (const int8_t *)t.bc_fwd;
+    v->d_bc_bwd = (const int8_t *)t.bc_bwd;
+    v->d_dir_fwd = (const int8_t *)t.dir_fwd;
+    v->d_dir_bwd = (const int8_t *)t.dir_bwd;
+    v->stream = (void *)ctx->stream;
+    return RT_OK;
+}
+
+extern "C" int rt_quadrature_device(rt_ctx *ctx, rt_quad_view *v, double *omega_host) {
+    if (!ctx || !v) return RT_ERR_ARG;
+    if (ctx->n2 < 2) return fail(ctx, RT_ERR_NOT_TRACED, "rt_quadrature_device: call rt_trace first");
+    CK(cudaSetDevice(ctx->device));
+    const int n2 = ctx->n2;
+    CK(ensure(ctx->b_omega, sizeof(double) * (size_t)n2));
+    const double *ad = (const double *)ctx->b_ang_d.p;
+    k_weights<<<blocks_for(n2 / 2, 64), 64, 0, ctx->stream>>>(n2, ad, (double *)ctx->b_omega.p);
+    CK(cudaGetLastError());
+    v->n_azim_2 = n2;
+    v->d_phi = ad;
+    v->d_sin = ad + n2;
+    v->d_cos = ad + 2 * n2;
+    v->d_delta_eff = ctx->has_delta ? ad + 6 * n2 : nullptr;
+    v->d_omega = (const double *)ctx->b_omega.p;
+    if (omega_host) CK(cudaMemcpyAsync(omega_host, ctx->b_omega.p, sizeof(double) * (size_t)n2, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+extern "C" int rt_optical_lengths(rt_ctx *ctx, int32_t n_groups, const double *sigma_t, int32_t layout, const double **d_tau,
+                                  double *tau_host) {
+    if (!ctx || n_groups < 1 || !sigma_t || (layout != 0 && layout != 1)) return fail(ctx, RT_ERR_ARG, "rt_optical_lengths: bad arguments");
+    if (!ctx->segmented) return fail(ctx, RT_ERR_ARG, "rt_optical_lengths: call rt_segmentize first");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const long long n_seg = ctx->res_nseg;
+    const size_t n_sig = (size_t)ctx->m.n_cells * (size_t)n_groups, n_tau = (size_t)std::max<long long>(n_seg, 1) * (size_t)n_groups;
+    CK(ensure(ctx->b_sigma, sizeof(double) * n_sig));
+    CK(ensure(ctx->b_tau, sizeof(double) * n_tau));
+    CK(cudaMemcpyAsync(ctx->b_sigma.p, sigma_t, sizeof(double) * n_sig, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev2[0], st));
+    if (n_seg > 0)
+        k_tau<<<blocks_for(n_seg * n_groups, 256), 256, 0, st>>>(n_seg, n_groups, ctx->s_len, ctx->s_elem, (const double *)ctx->b_sigma.p,
+                                                               layout, (double *)ctx->b_tau.p);
+    CK(cudaEventRecord(ctx->ev2[1], st));
+    CK(cudaGetLastError());
+    if (tau_host && n_seg > 0)
+        CK(cudaMemcpyAsync(tau_host, ctx->b_tau.p, sizeof(double) * (size_t)n_seg * n_groups, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev2[0], ctx->ev2[1]);
+    ctx->tau_ms = ms;
+    if (d_tau) *d_tau = (const double *)ctx->b_tau.p;
+    return RT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // volumes + NCCL
 // ------------------------------------------------------------------------------------------------------
 static int load_nccl(rt_ctx *ctx) {
@@ -1265,6 +1344,8 @@ extern "C" int rt_info(rt_ctx *ctx, const char *key, double *value) {
         *value = ctx->verify_fallbacks;
     else if (k == "eval_ms")
         *value = ctx->eval_ms;
+    else if (k == "tau_ms")
+        *value = ctx->tau_ms;
     else if (k == "n_units")
         *value = (double)ctx->n_units;
     else if (k == "segment_capacity")

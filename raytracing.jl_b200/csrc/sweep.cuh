@@ -1,0 +1,47 @@
+// sweep.cuh -- what a transport sweep (NeutronTransport.jl, reference README.md:9,125-136) consumes besides the Segment
+// records, produced and kept on the device:
+//   * azimuthal weights  init_weights!  (src/azimuthal_quad.jl:35-53)
+//   * optical lengths    tau[s][g] = sigma_t[element(s)][g] * len(s)   -- the `tau::Vector{T}` field of every Segment
+//     (src/segment.jl:27), which the reference leaves empty for the transport code to fill
+#pragma once
+#include "geom.cuh"
+
+namespace rt {
+
+// one thread per i in 1..N4 (0-based here); phi has N2 = 2*N4 entries; omega[i] = omega[N2-1-i]
+__global__ void k_weights(int n2, const double *phi, double *omega) {
+    const int n4 = n2 / 2;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0-based: reference i = this + 1
+    if (i >= n4) return;
+    double v;
+    if (i == 0)  // isone(i), tested first (src/azimuthal_quad.jl:41)
+        v = phi[1] - phi[0];
+    else if (i == n4 - 1)
+        v = kPi - phi[i] - phi[i - 1];
+    else
+        v = phi[i + 1] - phi[i - 1];
+    v = v / (4.0 * kPi);
+    omega[i] = v;
+    omega[n2 - 1 - i] = v;
+}
+
+// segment-major (layout 0: tau[s*G + g], the concatenation of the reference's per-segment vectors) or group-major
+// (layout 1: tau[g*S + s], unit-stride over segments for a sweep that runs one group at a time)
+__global__ void k_tau(long long n_seg, int n_groups, const double *__restrict__ len, const int *__restrict__ element,
+                      const double *__restrict__ sigma_t /* n_cells x n_groups */, int layout, double *__restrict__ tau) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_seg * n_groups) return;
+    long long s;
+    int g;
+    if (layout == 0) {
+        s = i / n_groups;
+        g = (int)(i - s * n_groups);
+    } else {
+        g = (int)(i / n_seg);
+        s = i - (long long)g * n_seg;
+    }
+    const int e = element[s] - 1;
+    tau[i] = sigma_t[(long long)e * n_groups + g] * len[s];
+}
+
+}  // namespace rt

@@ -292,6 +292,41 @@ def test_device_side_ingestion(pincell_model, which):
     assert_volumes_close(otg, tg)
 
 
+def test_sweep_facing_device_views(pincell_model):
+    """what a transport sweep consumes stays on the device -- track linkage (rt_tracks_device), azimuthal weights
+    computed on the device (rt_quadrature_device) and per-segment optical lengths tau = sigma_t[element] * len
+    (rt_optical_lengths, the Segment.tau field the reference leaves empty)."""
+    import torch
+
+    bcs = (0, 1, 2, 1)
+    tg = rt.TrackGenerator(pincell_model, 16, 0.05, bcs=bcs_of(bcs))
+    rt.segmentize_(rt.trace_(tg))
+    # linkage: the device arrays equal the downloaded track table, which equals the oracle's (test_trace_matches_oracle_bitwise)
+    v, t = tg.track_view(), tg.track_data
+    assert v["uid_begin"] == 1 and v["n_tracks"] == tg.n_total_tracks
+    dev = {k: torch.as_tensor(c, device="cuda").cpu().numpy() for k, c in v.items() if isinstance(c, api.DeviceColumn)}
+    assert np.array_equal(dev["px"], t["p"][:, 0]) and np.array_equal(dev["qy"], t["q"][:, 1]) and np.array_equal(dev["len"], t["len"])
+    assert np.array_equal(np.stack([dev["a"], dev["b"], dev["c"]], 1), t["abc"])
+    assert np.array_equal(dev["azim"] + 1, t["azim_idx"]) and np.array_equal(dev["track_idx"], t["track_idx"])
+    for k in ("next_fwd", "next_bwd", "bc_fwd", "bc_bwd", "dir_fwd", "dir_bwd"):
+        assert np.array_equal(dev[k], t[k]), k
+    # weights: bit-identical to init_weights! on the host (src/azimuthal_quad.jl:35-53; the reference's formula as it stands)
+    omega, qv = tg.quadrature_device()
+    assert np.array_equal(omega, tg.azimuthal_quadrature.weights) and np.all(omega > 0) and np.array_equal(omega, omega[::-1])
+    assert np.array_equal(torch.as_tensor(qv["omega"], device="cuda").cpu().numpy(), omega)
+    assert np.array_equal(torch.as_tensor(qv["delta_eff"], device="cuda").cpu().numpy(), tg.azimuthal_quadrature.deltas)
+    # optical lengths, both layouts, 7 groups (C5G7)
+    rng = np.random.default_rng(3)
+    sigma = rng.uniform(0.1, 2.0, size=(pincell_model.num_cells, 7))
+    s = tg.segments
+    ref = sigma[s["element"] - 1] * s["len"][:, None]
+    tau0, d0 = tg.optical_lengths(sigma, layout=0)
+    assert np.array_equal(tau0, ref)
+    assert np.array_equal(torch.as_tensor(d0, device="cuda").cpu().numpy().reshape(-1, 7), ref)
+    tau1, _ = tg.optical_lengths(sigma, layout=1)
+    assert np.array_equal(tau1, ref.T)
+
+
 def test_shard_planner_matches_device(pincell_model):
     from raytracing_jl_b200 import _lib
     from raytracing_jl_b200.api import _angle_tables
