@@ -54,14 +54,15 @@ def peaks():
 
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The timed region of the default run
-    is only tens of milliseconds, so the clocks are polled through NVML every 2 ms from a thread of this process (nvidia-smi
-    -lms cannot sample faster than ~100 ms); nvidia-smi is the fallback when NVML is unavailable."""
+    is only tens of milliseconds, so the clocks are polled through NVML every 10 ms from a thread of this process (nvidia-smi
+    -lms cannot sample faster than ~100 ms, and polling NVML faster than this measurably delays the kernel launches of the
+    timed loop); nvidia-smi is the fallback when NVML is unavailable."""
 
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
-        self.index, self.sm, self.reasons, self.mx = index, [], set(), None
+    def __init__(self, index, period=0.01):
+        self.index, self.sm, self.reasons, self.mx, self.period = index, [], set(), None, period
         self._stop, self._thr, self.how = threading.Event(), None, None
 
     def _nvml_loop(self):
@@ -77,7 +78,7 @@ class ClockSampler:
             for name, bit in bits.items():
                 if r & bit:
                     self.reasons.add(name)
-            time.sleep(0.002)
+            self._stop.wait(self.period)
 
     def _smi_loop(self):
         while not self._stop.is_set():
@@ -102,7 +103,7 @@ class ClockSampler:
             ids = [int(v) for v in vis.split(",") if v.strip().isdigit()]
             if ids and self.index < len(ids):
                 self.index = ids[self.index]
-            self.how, target = "nvml 2 ms", self._nvml_loop
+            self.how, target = f"nvml {int(self.period * 1e3)} ms", self._nvml_loop
         except Exception:
             self.how, target = "nvidia-smi", self._smi_loop
         self._thr = threading.Thread(target=target, daemon=True)
@@ -177,12 +178,13 @@ def workload_config(args, model, n_azim, delta):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="cfg3")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--clock-period-ms", type=float, default=10.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -220,7 +222,7 @@ def main():
 
     for _ in range(args.warmup):
         step()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, period=args.clock_period_ms * 1e-3)
     sampler.start()
     barrier()
     tg.timer_start()

@@ -88,11 +88,11 @@ struct rt_ctx {
     int opt_debug_verify_fail = 0;     // test hook: make the verification of the two-stage pipeline fail
     double eval_ms = 0.0, tau_ms = 0.0;
     cudaEvent_t ev2[2] = {nullptr, nullptr};
-    int opt_order_grid = 16;           // G x G tiles (0: identity order)
+    int opt_order_grid = 32;           // G x G tiles (0: identity order)
     int n_sm = 148;
     int opt_eval_waves = 1;            // k_eval2 grid = n_sm * resident blocks * this
     long long n_units = 0;
-    double opt_chunk_segments = 64.0;               // minimum expected segments per chunk
+    double opt_chunk_segments = 128.0;              // minimum expected segments per chunk
     double opt_target_walkers = 148.0 * 2048.0 * 4.0;  // chunks are sized so that about this many walkers exist
     double sum_len = 0.0;              // total track length of the shard
     double edge_sum = 0.0, area = 0.0;  // mesh density scalars (chunk sizing)

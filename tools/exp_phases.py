@@ -20,9 +20,9 @@ print("tracks", tg.n_total_tracks, "cells", model.num_cells)
 
 
 def run(label, flags=0, reps=3, **opts):
-    tg.set_option("chunk_segments", opts.get("chunk_segments", 64))
+    tg.set_option("chunk_segments", opts.get("chunk_segments", 128))
     tg.set_option("target_walkers", opts.get("target_walkers", 148 * 2048 * 4))
-    tg.set_option("order_grid", opts.get("order_grid", 16))
+    tg.set_option("order_grid", opts.get("order_grid", 32))
     tg.set_option("pipeline", opts.get("pipeline", 0))
     tg.set_option("eval_waves", opts.get("eval_waves", int(os.environ.get("RT_EVAL_WAVES", "1"))))
     best = None
