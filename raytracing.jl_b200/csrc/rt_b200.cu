@@ -16,6 +16,8 @@
 #include "scan.cuh"
 #include "sweep.cuh"
 #include "eval.cuh"
+#include "eval3.cuh"
+#include "march.cuh"
 #include "topo.cuh"
 #include "trace.cuh"
 
@@ -82,9 +84,15 @@ struct rt_ctx {
     long long *h_pin = nullptr;  // page-locked scratch for the small device->host read-backs of rt_segmentize (16 words)
     DevBuf b_scratch, b_gcounts, b_gcursor;  // rt_mesh_upload staging (kept between uploads)
     DevBuf b_rec, b_verify, b_tsum;    // two-stage pipeline: per-segment records, verification flag, per-track length sums
-    int opt_pipeline = 0;              // 0: hybrid (sign-test count walk + geometric fill walk), 1: sequential (walk.cuh only),
+    DevBuf b_pool, b_pool_next, b_pool_cursor;  // single-walk pipeline: record blocks (walk.cuh kRecBlock), chain, cursor
+    int count_batches = 0;             // single-walk pipeline: how many uid batches the count walk needed (info)
+    int opt_march = 1;                 // single-walk pipeline: k_march (register-resident loop) instead of k_topo<2>
+    long long opt_pool_slots = 0;      // test hook: at most this many chunk slots per count batch (0: as many as fit)
+    double opt_pool_extra = 1.25;      // spare pool blocks, as a multiple of (expected segments / kRecBlock)
+    int opt_pipeline = 3;              // 3: single walk (k_march counts AND records, k_eval3 evaluates) [default]; 0: hybrid (sign-test count walk + geometric fill walk), 1: sequential (walk.cuh only),
                                        // 2: two-stage (sign-test walks + one thread per segment); 0 and 2 fall back to 1
     int verify_fallbacks = 0;
+    int fallback_mode = 1;             // pipeline to repeat the call with after a failed verification
     int opt_debug_verify_fail = 0;     // test hook: make the verification of the two-stage pipeline fail
     double eval_ms = 0.0, tau_ms = 0.0;
     cudaEvent_t ev2[2] = {nullptr, nullptr};
@@ -150,14 +158,14 @@ static void release(DevBuf &b) {
 static inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 template <typename Tin, typename Tout>
-static cudaError_t exclusive_scan(rt_ctx *ctx, const Tin *in, Tout *out, long long n) {
+static cudaError_t exclusive_scan(rt_ctx *ctx, const Tin *in, Tout *out, long long n, Tout carry = Tout(0)) {
     long long n_tiles = (n + kScanTile - 1) / kScanTile;
     cudaError_t e = ensure(ctx->b_tile, sizeof(Tout) * (size_t)n_tiles);
     if (e != cudaSuccess) return e;
     Tout *tiles = (Tout *)ctx->b_tile.p;
     k_scan_tile_sums<Tin, Tout><<<(unsigned)n_tiles, kScanThreads, 0, ctx->stream>>>(in, tiles, n);
     k_scan_tile_offsets<Tout><<<1, kScanThreads, 0, ctx->stream>>>(tiles, n_tiles);
-    k_scan_apply<Tin, Tout><<<(unsigned)n_tiles, kScanThreads, 0, ctx->stream>>>(in, out, tiles, n);
+    k_scan_apply<Tin, Tout><<<(unsigned)n_tiles, kScanThreads, 0, ctx->stream>>>(in, out, tiles, n, carry);
     return cudaGetLastError();
 }
 
@@ -207,7 +215,8 @@ extern "C" void rt_destroy(rt_ctx *ctx) {
                      &ctx->b_nch,     &ctx->b_blk_chunks, &ctx->b_unit_base, &ctx->b_unit_block, &ctx->b_ch_i, &ctx->b_ch_d,
                      &ctx->b_order,   &ctx->b_okeys,      &ctx->b_ohist,     &ctx->b_rec,     &ctx->b_verify,    &ctx->b_tsum,      &ctx->b_evalblk,   &ctx->b_trkrec,
                      &ctx->b_scratch, &ctx->b_gcounts,   &ctx->b_gcursor,
-                     &ctx->b_omega,   &ctx->b_sigma,     &ctx->b_tau};
+                     &ctx->b_omega,   &ctx->b_sigma,     &ctx->b_tau,
+                     &ctx->b_pool,    &ctx->b_pool_next, &ctx->b_pool_cursor};
     for (DevBuf *b : all) release(*b);
     for (int ph = 0; ph < 6; ++ph)
         for (int q = 0; q < 2; ++q)
@@ -710,11 +719,232 @@ static double lmin_of(const DevMesh &m, double tiny_step) {
     return fmax(8.0 * tiny_step, kRtol * nb * (1.0 + 1e-6) + 1e-300);
 }
 
+// ---- single-walk pipeline (mode 3): k_topo<2> counts AND records every chunk in one walk, k_eval3 evaluates the records -------
+// The records live in a pool of kRecBlock-record blocks: block i < slots is the first block of chunk slot i of the batch, the
+// blocks behind are claimed by the walkers as they need them.  Shards whose pool would not fit next to the Segment columns are
+// processed in uid batches (whole 32-track blocks): count+record a batch, scan its offsets (carrying the running total), then
+// evaluate it -- in sub-batches when its segments exceed the resident capacity.  *next_mode = 0 asks the caller to repeat the
+// call with the hybrid pipeline (pool exhausted: the mesh is far denser along some chunks than the Cauchy-Crofton estimate).
+static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_vol, rt_batch_cb cb, void *cb_user, int attempt,
+                             bool *verify_failed, int *next_mode, double *launches_io, double est_total) {
+    cudaStream_t st = ctx->stream;
+    const long long n = ctx->n_shard;
+    const long long n_blocks = (n + 31) / 32;
+    const long long n_units = P.ch.n_units;
+    const size_t nn = (size_t)std::max<long long>(n, 1);
+    double launches = 0;
+    const int *order_all = P.ch.order;
+    CK(ensure(ctx->b_tsum, sizeof(double) * nn));
+    CK(cudaMemsetAsync(ctx->b_tsum.p, 0, sizeof(double) * nn, st));
+    CK(ensure(ctx->b_pool_cursor, sizeof(int)));
+    P.tsum = (double *)ctx->b_tsum.p;
+    P.pool_cursor = (int *)ctx->b_pool_cursor.p;
+    const double lmin_eval = ctx->opt_debug_verify_fail ? INFINITY : P.lmin;
+
+    // ---- memory plan
+    size_t free_b = 0, total_b = 0;
+    bool have_mem = false;
+    auto query_mem = [&]() -> cudaError_t {
+        if (have_mem) return cudaSuccess;
+        have_mem = true;
+        return cudaMemGetInfo(&free_b, &total_b);
+    };
+    const long long slots_all = n_units * 32;
+    const double extra_per_slot = est_total * ctx->opt_pool_extra / kRecBlock / (double)std::max<long long>(slots_all, 1);
+    const size_t block_bytes = sizeof(int) * (kRecBlock + 1);  // records + chain entry
+    const long long spare = ctx->opt_pool_extra > 0.0 ? 4096 : 0;
+    auto blocks_for_slots = [&](long long slots) { return slots + (long long)((double)slots * extra_per_slot) + spare; };
+    long long max_slots = slots_all;
+    if (ctx->opt_pool_slots > 0) max_slots = std::min(max_slots, std::max<long long>(32, ctx->opt_pool_slots & ~31LL));
+    const size_t pool_have = std::min<size_t>(ctx->b_pool.bytes / (sizeof(int) * kRecBlock), ctx->b_pool_next.bytes / sizeof(int));
+    if ((size_t)blocks_for_slots(std::min(max_slots, slots_all)) > pool_have) {
+        CK(query_mem());
+        const size_t avail = free_b + ctx->b_pool.bytes + ctx->b_pool_next.bytes + ctx->b_seg_d.bytes + ctx->b_seg_e.bytes;
+        const size_t budget = (size_t)((double)avail * 0.15);  // ~9 pool bytes next to 44 Segment bytes per segment
+        if ((size_t)blocks_for_slots(std::min(max_slots, slots_all)) * block_bytes > budget) {
+            max_slots = (long long)((double)budget / ((double)block_bytes * (1.0 + extra_per_slot))) - 8192;
+            max_slots &= ~31LL;
+        }
+        const long long pb = blocks_for_slots(std::min(max_slots, slots_all));
+        if (max_slots < 32 || pb >= (1LL << 31)) {
+            *next_mode = 0;
+            *verify_failed = true;
+            return RT_OK;
+        }
+        if ((size_t)pb > pool_have) {
+            if (max_slots < slots_all) {  // the Segment columns are re-fitted to what the pool leaves
+                release(ctx->b_seg_d);
+                release(ctx->b_seg_e);
+                ctx->cap = 0;
+            }
+            release(ctx->b_pool);
+            release(ctx->b_pool_next);
+            CK(ensure(ctx->b_pool, sizeof(int) * (size_t)pb * kRecBlock));
+            CK(ensure(ctx->b_pool_next, sizeof(int) * (size_t)pb));
+            have_mem = false;
+        }
+    }
+    P.pool = (int *)ctx->b_pool.p;
+    P.pool_next = (int *)ctx->b_pool_next.p;
+    P.pool_blocks = (int)std::min<size_t>(ctx->b_pool.bytes / (sizeof(int) * kRecBlock), ctx->b_pool_next.bytes / sizeof(int));
+    if (ctx->opt_pool_extra <= 0.0) P.pool_blocks = (int)std::min<long long>(P.pool_blocks, blocks_for_slots(std::min(max_slots, slots_all)));
+
+    const bool multi = max_slots < slots_all;
+    std::vector<long long> h_unit_base;
+    if (multi || ctx->cap_cfg > 0) {
+        h_unit_base.resize((size_t)n_blocks + 1);
+        CK(cudaMemcpyAsync(h_unit_base.data(), ctx->b_unit_base.p, sizeof(long long) * h_unit_base.size(), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    std::vector<long long> h_off;
+    long long base = 0;  // segments of the batches already done
+    long long B0 = 0;
+    ctx->count_batches = 0;
+    ctx->phase_ms[4] = 0.0;
+    while (B0 < n_blocks) {
+        long long B1 = n_blocks;
+        if (multi) {
+            const long long lim = h_unit_base[(size_t)B0] + max_slots / 32;
+            B1 = (long long)(std::upper_bound(h_unit_base.begin() + B0, h_unit_base.end(), lim) - h_unit_base.begin()) - 1;
+            if (B1 <= B0) return fail(ctx, RT_ERR_NOMEM, "rt_segmentize: one block of 32 tracks needs more than the record pool");
+        }
+        const long long b = 32 * B0, e = std::min(32 * B1, n);
+        const long long u0 = multi ? h_unit_base[(size_t)B0] : 0, u1 = multi ? h_unit_base[(size_t)B1] : n_units;
+        const long long slots = (u1 - u0) * 32;
+        ctx->count_batches += 1;
+        // ---- seeds, count+record walk, per-track fix-up, offsets of the batch
+        P.trk_begin = b;
+        P.trk_end = e;
+        P.unit_begin = u0;
+        P.unit_end = u1;
+        P.ch.order = multi ? nullptr : order_all;
+        P.pool_slot_base = u0 * 32;
+        P.vol = nullptr;
+        P.offset_base = 0;
+        ctx->h_pin[8] = 0;
+        *(int *)&ctx->h_pin[8] = (int)slots;
+        CK(cudaMemcpyAsync(P.pool_cursor, &ctx->h_pin[8], sizeof(int), cudaMemcpyHostToDevice, st));
+        k_seed<<<blocks_for(slots, 128), 128, 0, st>>>(P);
+        if (ctx->opt_march)
+            k_march<<<blocks_for(slots, kMarchThreads), kMarchThreads, 0, st>>>(P);
+        else
+            k_topo<2><<<blocks_for(slots, kTopoThreads), kTopoThreads, 0, st>>>(P);
+        k_fixup_tracks<<<blocks_for(e - b, 128), 128, 0, st>>>(P);
+        CK(cudaGetLastError());
+        if (B0 == 0) toc(ctx, 2);
+        if (B0 == 0) tic(ctx, 3);
+        CK((exclusive_scan<int, long long>(ctx, (const int *)ctx->b_count.p + b, (long long *)ctx->b_offsets.p + b, e - b, base)));
+        if (B0 == 0) toc(ctx, 3);
+        launches += 6;
+        CK(cudaMemcpyAsync(&ctx->h_pin[1], (long long *)ctx->b_offsets.p + e, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&ctx->h_pin[9], P.pool_cursor, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const long long batch_total = ctx->h_pin[1] - base;
+        if ((long long)*(int *)&ctx->h_pin[9] > (long long)P.pool_blocks) {  // some walker found the pool empty
+            *next_mode = 0;
+            *verify_failed = true;
+            return RT_OK;
+        }
+        ctx->total_segments = base + batch_total;
+        // ---- Segment columns: everything of this batch if it fits, else as much as fits
+        long long want = batch_total;
+        if (ctx->cap_cfg > 0) want = std::min(want, (long long)ctx->cap_cfg);
+        if (want > ctx->cap || !ctx->b_seg_d.p) {
+            CK(query_mem());
+            const long long fit = (long long)((double)(free_b + ctx->b_seg_d.bytes + ctx->b_seg_e.bytes) * 0.92 / 44.0);
+            long long cap = std::min(multi ? std::max(want, fit) : want, fit);
+            if (ctx->cap_cfg > 0) cap = std::min(cap, (long long)ctx->cap_cfg);
+            int rc = ensure_segment_buffers(ctx, cap);
+            if (rc) return rc;
+            have_mem = false;
+        }
+        const long long cap = ctx->cap_cfg > 0 ? std::min(ctx->cap, (long long)ctx->cap_cfg) : ctx->cap;
+        P.opx = ctx->s_px;
+        P.opy = ctx->s_py;
+        P.oqx = ctx->s_qx;
+        P.oqy = ctx->s_qy;
+        P.olen = ctx->s_len;
+        P.oelem = ctx->s_elem;
+        P.vol = want_vol ? (double *)ctx->b_vol.p : nullptr;
+        EvalParams E{};
+        E.m = P.m;
+        E.t = ctx->t;
+        E.ang = P.ang;
+        E.offsets = P.offsets;
+        E.n_tracks = n;
+        E.olen = P.olen;
+        E.status = P.status;
+        E.tsum = P.tsum;
+        E.rtol = rtol;
+        const bool split = batch_total > cap;
+        if (split) {
+            h_off.resize((size_t)(e - b) + 1);
+            CK(cudaMemcpyAsync(h_off.data(), (long long *)ctx->b_offsets.p + b, sizeof(long long) * h_off.size(), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        if (B0 == 0) tic(ctx, 4);
+        long long sb = b;
+        while (sb < e) {
+            long long se = e;
+            if (split) {
+                const long long lim = h_off[(size_t)(sb - b)] + cap;
+                se = b + (long long)(std::upper_bound(h_off.begin() + (sb - b), h_off.end(), lim) - h_off.begin()) - 1;
+                if (se <= sb) return fail(ctx, RT_ERR_NOMEM, "rt_segmentize: one track needs more than the segment capacity");
+            }
+            const long long off_b = split ? h_off[(size_t)(sb - b)] : base;
+            const long long nseg_b = (split ? h_off[(size_t)(se - b)] : base + batch_total) - off_b;
+            P.trk_begin = sb;
+            P.trk_end = se;
+            P.offset_base = off_b;
+            if (split) {  // the warp units of the 32-track blocks overlapping [sb, se), in identity order
+                P.ch.order = nullptr;
+                P.unit_begin = h_unit_base[(size_t)(sb >> 5)];
+                P.unit_end = h_unit_base[(size_t)((se - 1) >> 5) + 1];
+            }
+            WalkParams PE = P;
+            PE.lmin = lmin_eval;
+            if (nseg_b > 0)
+                k_eval3<<<blocks_for((PE.unit_end - PE.unit_begin) * 32 * 32, kEval3Threads), kEval3Threads, 0, st>>>(PE);
+            E.trk_begin = sb;
+            E.trk_end = se;
+            E.offset_base = off_b;
+            E.n_seg = nseg_b;
+            if (se > sb) k_track_status<<<blocks_for(se - sb, 128), 128, 0, st>>>(E);
+            launches += 2;
+            CK(cudaGetLastError());
+            ctx->res_trk_begin = sb;
+            ctx->res_trk_end = se;
+            ctx->res_off_base = off_b;
+            ctx->res_nseg = nseg_b;
+            if (B0 == 0 && se == e) toc(ctx, 4);
+            ctx->h_pin[2] = 0;
+            CK(cudaMemcpyAsync(&ctx->h_pin[2], ctx->b_verify.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if ((int)ctx->h_pin[2]) {
+                *verify_failed = true;
+                return RT_OK;
+            }
+            if (cb) {
+                rt_batch bt;
+                int rcb = rt_segments_device(ctx, &bt);
+                if (rcb) return rcb;
+                bt.attempt = attempt;
+                if (cb(&bt, cb_user)) return fail(ctx, RT_ERR_ARG, "rt_segmentize: batch callback asked to stop");
+            }
+            sb = se;
+        }
+        base += batch_total;
+        B0 = B1;
+    }
+    *launches_io += launches;
+    return RT_OK;
+}
+
 // One complete count -> scan -> fill execution.
 //   mode 1 (sequential): k_walk<false> counts, k_walk<true> fills (walk.cuh);
-//   mode 0 (hybrid):     k_topo<false> counts by sign tests (topo.cuh), k_walk<true> fills and re-derives the same decisions
+//   mode 0 (hybrid):     k_topo<0> counts by sign tests (topo.cuh), k_walk<true> fills and re-derives the same decisions
 //                        from the exact geometry;
-//   mode 2 (two-stage):  k_topo<false> counts, k_topo<true> writes per-segment records, k_eval evaluates one segment per thread.
+//   mode 2 (two-stage):  k_topo<0> counts, k_topo<1> writes per-segment records, k_eval evaluates one segment per thread.
 // In modes 0 and 2 the length check (src/track.jl:171-175) runs after the fill (k_track_status).  *verify_failed reports that
 // the fill disagreed with the count (mode 0) or that a segment broke a geometric fast-path condition (mode 2): the caller then
 // repeats the call in mode 1.
@@ -723,6 +953,8 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
     const bool topo = mode == 2, topo_count = mode != 1;
     cudaStream_t st = ctx->stream;
     const long long n = ctx->n_shard;
+    const bool single = mode == 3 && n > 0;
+    double est_total_segments = 0.0;
     const int n2 = ctx->n2;
     DevMesh &m = ctx->m;
     const bool want_vol = !(flags & RT_SEG_NO_VOLUMES);
@@ -769,6 +1001,7 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         const long long n_blocks = (n + 31) / 32;
         double rho = ctx->edge_sum / (kPi * ctx->area);  // expected cell crossings per unit track length
         double est_total = ctx->sum_len * rho;
+        est_total_segments = est_total;
         double seg_target = fmax(ctx->opt_chunk_segments, est_total / ctx->opt_target_walkers);
         double chunk_len = (flags & RT_SEG_NO_CHUNKS) || !(rho > 0.0) ? INFINITY : seg_target / rho;
         CK(ensure(ctx->b_nch, sizeof(int) * (size_t)n));
@@ -825,39 +1058,61 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         }
         // ---- seeds, count pass, per-track fix-up
         P.vol = nullptr;
+        if (single) {
+            // (the single-walk pipeline runs them per uid batch, see segmentize_single)
+        } else {
         k_seed<<<blocks_for(n_units * 32, 128), 128, 0, st>>>(P);
         if (topo_count) {
-            k_topo<false><<<blocks_for(n_units * 32, kTopoThreads), kTopoThreads, 0, st>>>(P);
+            k_topo<0><<<blocks_for(n_units * 32, kTopoThreads), kTopoThreads, 0, st>>>(P);
         } else {
             P.vol = (want_vol && count_only) ? (double *)ctx->b_vol.p : nullptr;
             k_walk<false><<<blocks_for(n_units * 32, kWalkThreads), kWalkThreads, 0, st>>>(P);
         }
         k_fixup_tracks<<<blocks_for(n, 128), 128, 0, st>>>(P);
         launches += 3;
+        }
     }
     CK(cudaGetLastError());
-    toc(ctx, 2);
+    if (single) {
+        ctx->res_trk_begin = ctx->res_trk_end = 0;
+        ctx->res_off_base = 0;
+        ctx->res_nseg = 0;
+        ctx->eval_ms = 0.0;
+        P.counters = (unsigned long long *)ctx->b_counters.p;
+        int next_mode = 1;
+        int rc = segmentize_single(ctx, P, rtol, want_vol, cb, cb_user, attempt, verify_failed, &next_mode, &launches, est_total_segments);
+        if (rc) return rc;
+        if (*verify_failed) {
+            ctx->fallback_mode = next_mode;
+            return RT_OK;
+        }
+    }
+    if (!single) toc(ctx, 2);
     // ---- scan
-    tic(ctx, 3);
+    if (!single) tic(ctx, 3);
     long long total = 0;
-    if (n > 0) {
+    if (n > 0 && !single) {
         CK((exclusive_scan<int, long long>(ctx, (const int *)ctx->b_count.p, (long long *)ctx->b_offsets.p, n)));
         launches += 3;
         CK(cudaMemcpyAsync(&ctx->h_pin[1], (long long *)ctx->b_offsets.p + n, sizeof(long long), cudaMemcpyDeviceToHost, st));
     }
-    toc(ctx, 3);
-    CK(cudaStreamSynchronize(st));
-    if (n > 0) total = ctx->h_pin[1];
-    ctx->total_segments = total;
+    if (!single) {
+        toc(ctx, 3);
+        CK(cudaStreamSynchronize(st));
+        if (n > 0) total = ctx->h_pin[1];
+        ctx->total_segments = total;
+    }
 
     // ---- fill pass (possibly in uid batches over a recycled buffer)
-    ctx->phase_ms[4] = 0.0;
-    ctx->pev_dirty[4] = false;
-    ctx->eval_ms = 0.0;
-    ctx->res_trk_begin = ctx->res_trk_end = 0;
-    ctx->res_off_base = 0;
-    ctx->res_nseg = 0;
-    if (!count_only && n > 0) {
+    if (!single) {
+        ctx->phase_ms[4] = 0.0;
+        ctx->pev_dirty[4] = false;
+        ctx->eval_ms = 0.0;
+        ctx->res_trk_begin = ctx->res_trk_end = 0;
+        ctx->res_off_base = 0;
+        ctx->res_nseg = 0;
+    }
+    if (!count_only && n > 0 && !single) {
         long long cap = total;
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
@@ -934,7 +1189,7 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
             }
             const long long nseg_b = (total > cap ? h_off[e] : total) - P.offset_base;
             if (topo) {
-                k_topo<true><<<blocks_for((P.unit_end - P.unit_begin) * 32, kTopoThreads), kTopoThreads, 0, st>>>(P);
+                k_topo<1><<<blocks_for((P.unit_end - P.unit_begin) * 32, kTopoThreads), kTopoThreads, 0, st>>>(P);
                 E.trk_begin = b;
                 E.trk_end = e;
                 E.offset_base = P.offset_base;
@@ -1057,12 +1312,16 @@ extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rt
     ctx->stats[0] = 0;
     ctx->verify_fallbacks = 0;
     unsigned long long bad = ~0ULL;
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    if (mode == 3 && (flags & RT_SEG_LITERAL)) mode = 1;  // (literal-only walks have nothing to gain from per-segment evaluation)
+    for (int attempt = 0; attempt < 3; ++attempt) {
         bool vf = false;
+        ctx->fallback_mode = 1;
         int rc = segmentize_once(ctx, tiny_step, k, rtol, max_iter, flags, cb, cb_user, mode, attempt, &vf, &bad);
         if (rc) return rc;
         if (!vf) break;
-        mode = 1;  // count and fill disagreed / a geometric fast-path condition failed: redo everything sequentially
+        // count and fill disagreed / a geometric fast-path condition failed: redo everything sequentially (the single-walk
+        // pipeline asks for the hybrid one when its record pool ran out)
+        mode = ctx->fallback_mode;
         ctx->verify_fallbacks += 1;
     }
     if (n_segments_total) *n_segments_total = ctx->total_segments;
@@ -1350,6 +1609,8 @@ extern "C" int rt_info(rt_ctx *ctx, const char *key, double *value) {
         *value = (double)ctx->n_units;
     else if (k == "segment_capacity")
         *value = (double)ctx->cap;
+    else if (k == "count_batches")
+        *value = (double)ctx->count_batches;
     else
         return fail(ctx, RT_ERR_ARG, "rt_info: unknown key %s", key);
     return RT_OK;
@@ -1390,10 +1651,16 @@ extern "C" int rt_set_option(rt_ctx *ctx, const char *name, double value) {
         ctx->opt_target_walkers = value;
     else if (n == "order_grid" && value >= 0.0 && value <= 256.0)
         ctx->opt_order_grid = (int)value;
-    else if (n == "pipeline" && (value == 0.0 || value == 1.0 || value == 2.0))
+    else if (n == "pipeline" && (value == 0.0 || value == 1.0 || value == 2.0 || value == 3.0))
         ctx->opt_pipeline = (int)value;
     else if (n == "eval_waves" && value >= 1.0 && value <= 64.0)
         ctx->opt_eval_waves = (int)value;
+    else if (n == "march")
+        ctx->opt_march = value != 0.0;
+    else if (n == "pool_slots" && value >= 0.0)
+        ctx->opt_pool_slots = (long long)value;
+    else if (n == "pool_extra" && value >= 0.0)
+        ctx->opt_pool_extra = value;
     else if (n == "debug_verify_fail")
         ctx->opt_debug_verify_fail = value != 0.0;
     else

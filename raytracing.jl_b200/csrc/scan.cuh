@@ -1,6 +1,6 @@
 // scan.cuh -- exclusive prefix sums (per-track segment counts -> segment offsets; track lengths ->
 // shard split points).  Three small kernels: per-tile reduce, scan of the tile sums by one block, and
-// tile-local warp-shuffle scan + offset.  out has n+1 entries (out[n] = total).
+// tile-local warp-shuffle scan + offset (+ a caller-supplied carry).  out has n+1 entries (out[n] = carry + total).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_tile_offsets(Tout *tile_s
 
 template <typename Tin, typename Tout>
 __global__ void __launch_bounds__(kScanThreads) k_scan_apply(const Tin *in, Tout *out, const Tout *tile_offsets,
-                                                             long long n) {
+                                                             long long n, Tout carry) {
     __shared__ Tout total;
     long long base = blockIdx.x * (long long)kScanTile + threadIdx.x * kScanItems;
     Tout v[kScanItems];
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(const Tin *in, Tout
         v[q] = (base + q < n) ? (Tout)in[base + q] : Tout(0);
         s += v[q];
     }
-    Tout ex = block_excl_scan<Tout>(s, &total) + tile_offsets[blockIdx.x];
+    Tout ex = block_excl_scan<Tout>(s, &total) + tile_offsets[blockIdx.x] + carry;
 #pragma unroll
     for (int q = 0; q < kScanItems; ++q) {
         if (base + q < n) out[base + q] = ex;

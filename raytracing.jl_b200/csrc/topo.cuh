@@ -4,11 +4,11 @@
 // (src/intersection.jl:60).  So the serial part of _segmentize_track! (src/track.jl:106-178) is only the ORDER in which
 // cells are accepted; the geometry of every accepted cell can be evaluated independently afterwards.
 //
-//   k_topo<false>  count pass: walks the half-edge graph deciding each transition from the SIGNS of the signed distances of
+//   k_topo<0>  count pass: walks the half-edge graph deciding each transition from the SIGNS of the signed distances of
 //                  the cell's vertices from the track line (two multiply-adds per step, no division, no square root),
 //                  under the same clearance test as the sequential fast path (walk.cuh); everything that test does not
 //                  cover runs the literal walk of the reference, exactly as in walk.cuh.
-//   k_topo<true>   fill pass, stage 1: the same walk writes one 4-byte record per segment at its final position:
+//   k_topo<1>   fill pass, stage 1: the same walk writes one 4-byte record per segment at its final position:
 //                  fast:  (h << 2) | (exit1 << 1)   h = entry half-edge 3*cell + k, exit1: leaves through edge k+1 (else k+2)
 //                  literal: (cell << 2) | 1
 //   k_eval2        (eval.cuh) fill pass, stage 2: ONE THREAD PER SEGMENT, coalesced.  Fast records: p and q are the reference's
@@ -28,6 +28,12 @@ constexpr int kTopoThreads = 128;
 #define RT_TOPO_MIN_BLOCKS 8
 #endif
 
+// (the pool records are read back by k_eval3 within the same call: no eviction hint, they should stay in L2 if they fit)
+__device__ __forceinline__ void stg256_plain_i(void *p, const int *v) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+                 "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
 __device__ __forceinline__ void stg256_stream_i(void *p, unsigned long long pol, const int *v) {
     asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
                  "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "l"(pol)
@@ -61,11 +67,16 @@ __device__ __forceinline__ P2 exit_point(const DevMesh &m, const Line &trk, int 
     return X;
 }
 
-template <bool FILL>
+// MODE 0: count only; MODE 1: write the records at their final positions (needs the counts and offsets of an earlier MODE 0
+// pass); MODE 2: count AND record in one walk -- the records go to a pool of kRecBlock-record blocks (the chunk's first block
+// is implicit, further blocks are claimed with one atomic each and chained through pool_next), from where k_eval3 (eval3.cuh)
+// evaluates them once the scan has fixed the final positions.
+template <int MODE>
 __global__ void __launch_bounds__(kTopoThreads, RT_TOPO_MIN_BLOCKS) k_topo(const __grid_constant__ WalkParams P) {
+    constexpr bool FILL = MODE == 1, REC = MODE == 2;
     const unsigned FULL = 0xffffffffu;
     const DevMesh &m = P.m;
-    __shared__ int s_rec[FILL ? 8 * kTopoThreads : 1];  // fill: 8 records per thread = one 32-byte sector
+    __shared__ int s_rec[MODE != 0 ? 8 * kTopoThreads : 1];  // 8 records per thread = one 32-byte sector
     const int tid = threadIdx.x;
     long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
@@ -93,6 +104,8 @@ __global__ void __launch_bounds__(kTopoThreads, RT_TOPO_MIN_BLOCKS) k_topo(const
     bool active = false;
     const unsigned long long pol_keep = l2_policy_keep();
     const unsigned long long pol_stream = FILL ? l2_policy_stream() : 0ull;
+    int pb = REC ? (int)(cidx - P.pool_slot_base) : 0;  // MODE 2: block of the pool that is being filled
+    bool recording = REC;
     constexpr double kKappa = 1.0 / 64.0;  // smallest sine of a crossing angle the cheap filter accepts
     bool cheap_ok = false;                 // x-ordering of entry/exit is decided by the track direction, beyond rounding
     double ang_thr = 0.0;
@@ -163,6 +176,27 @@ __global__ void __launch_bounds__(kTopoThreads, RT_TOPO_MIN_BLOCKS) k_topo(const
     }
 
     auto push = [&](int e, int rec) {
+        if (REC && recording) {
+            if (nseg > 0 && (nseg & (kRecBlock - 1)) == 0) {  // the current block is full: claim the next one
+                const int nb = atomicAdd(P.pool_cursor, 1);
+                if (nb >= P.pool_blocks) {
+                    recording = false;  // pool exhausted (the host sees pool_cursor > pool_blocks and repeats the call with another pipeline)
+                } else {
+                    P.pool_next[pb] = nb;
+                    pb = nb;
+                }
+            }
+            if (recording) {
+                const int k = nseg & 7;
+                s_rec[k * kTopoThreads + tid] = rec;
+                if (k == 7) {
+                    int v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] = s_rec[q * kTopoThreads + tid];
+                    stg256_plain_i(P.pool + (long long)pb * kRecBlock + ((nseg & (kRecBlock - 1)) - 7), v);
+                }
+            }
+        }
         if (FILL) {
             long long o = out + nseg;
             int k = (int)(o & 7);
@@ -297,6 +331,11 @@ __global__ void __launch_bounds__(kTopoThreads, RT_TOPO_MIN_BLOCKS) k_topo(const
         }
     }
 
+    if (REC && recording && (nseg & 7)) {  // the incomplete last sector of this chunk's records
+        const int rem = nseg & 7;
+        int *dst = P.pool + (long long)pb * kRecBlock + (((nseg - 1) & (kRecBlock - 1)) - (rem - 1));
+        for (int kk = 0; kk < rem; ++kk) dst[kk] = s_rec[kk * kTopoThreads + tid];
+    }
     if (!FILL && t < P.n_tracks && j < P.ch.nch[t]) {
         P.ch.count[cidx] = active ? nseg : 0;
         P.ch.sum[cidx] = 0.0;

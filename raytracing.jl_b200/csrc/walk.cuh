@@ -73,7 +73,16 @@ struct WalkParams {
     int *rec;                      // two-stage pipeline (topo.cuh): per-segment records
     int *verify_fail;
     double *tsum;                  // two-stage pipeline: per-track sum of segment lengths
+    // single-walk pipeline (k_topo<2> + k_eval3): pool of record blocks
+    int *pool;                     // pool_blocks * kRecBlock records
+    int *pool_next;                // per block: the chunk's next block
+    int *pool_cursor;              // next unclaimed block
+    int pool_blocks;
+    long long pool_slot_base;      // chunk slot (unit*32 + lane) whose first block is block 0
 };
+
+constexpr int kRecBlock = 256;  // records per pool block (a multiple of 32): with the default chunks of ~128 segments a walker
+                                // rarely needs a second block, so the claiming atomic stays off the hot path
 
 enum { MODE_FAST = 0, MODE_SLOW = 1, MODE_DONE = 2 };
 constexpr int kFastBatch = 16;
@@ -616,8 +625,8 @@ __global__ void __launch_bounds__(kWalkThreads, RT_WALK_MIN_BLOCKS) k_walk(const
 //  * a chunk that ended with an error / at the track end / at the MAX_ITER cap ends the track: later chunks are dropped
 //  * the total is capped at max_iter (src/track.jl:119); the length check (src/track.jl:171-175) uses the chunk sums
 __global__ void k_fixup_tracks(const __grid_constant__ WalkParams P) {
-    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t >= P.n_tracks) return;
+    long long t = P.trk_begin + blockIdx.x * (long long)blockDim.x + threadIdx.x;  // tracks [trk_begin, trk_end) of the shard
+    if (t >= P.trk_end) return;
     int n = P.ch.nch[t];
     long long blk = t >> 5;
     int lane = (int)(t & 31);

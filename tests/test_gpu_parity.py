@@ -128,11 +128,12 @@ def test_pincell_segments_match_oracle(pincell_model, n_azim, delta, flags, chun
     assert_segments_equal(otg, tg)
     assert_volumes_close(otg, tg)
     assert otg.bad_status == 0
-    if not flags & SEQ:  # the other self-verifying pipeline (one thread per segment)
-        otg, tg = run_both(pincell_model, n_azim, delta, flags=flags, chunk_segments=chunk, pipeline=2)
-        assert_segments_equal(otg, tg)
-        assert_volumes_close(otg, tg)
-        assert tg.info("verify_fallbacks") == 0
+    if not flags & SEQ:  # the other self-verifying pipelines (one thread per segment: after a second walk / after a single walk)
+        for pipeline in (2, 3):
+            otg, tg = run_both(pincell_model, n_azim, delta, flags=flags, chunk_segments=chunk, pipeline=pipeline)
+            assert_segments_equal(otg, tg)
+            assert_volumes_close(otg, tg)
+            assert tg.info("verify_fallbacks") == 0
 
 
 def test_reference_invariants_on_gpu_result(pincell_model):  # test/runtests.jl:30-43
@@ -164,10 +165,11 @@ def test_jittered_mesh_matches_oracle(seed, n, n_azim, delta):
     otg, tg = run_both(model, n_azim, delta, flags=SEQ, chunk_segments=5)  # the sequential kernels on the same input
     assert_segments_equal(otg, tg)
     assert_volumes_close(otg, tg)
-    otg, tg = run_both(model, n_azim, delta, chunk_segments=5, pipeline=2)  # one thread per segment
-    assert_segments_equal(otg, tg)
-    assert_volumes_close(otg, tg)
-    assert tg.info("verify_fallbacks") == 0
+    for pipeline, chunk in ((2, 5), (3, 5), (3, None), (3, 600)):  # one thread per segment (3: records from the count walk itself)
+        otg, tg = run_both(model, n_azim, delta, chunk_segments=chunk, pipeline=pipeline)
+        assert_segments_equal(otg, tg)
+        assert_volumes_close(otg, tg)
+        assert tg.info("verify_fallbacks") == 0
 
 
 def test_offset_domain_and_rectangle():
@@ -207,7 +209,7 @@ def test_structured_mesh_exact_vertex_crossings():
     assert_segments_equal(otg, tg)
 
 
-@pytest.mark.parametrize("pipeline", [0, 1, 2])
+@pytest.mark.parametrize("pipeline", [0, 1, 2, 3])
 @pytest.mark.parametrize("chunk", [None, 7])
 def test_batched_fill_equals_single_shot(pincell_model, chunk, pipeline):
     otg, tg = run_both(pincell_model, 32, 0.01, capacity=20000, chunk_segments=chunk, pipeline=pipeline)
@@ -404,11 +406,11 @@ def test_cfg4_full_size_pipelines_agree():
     ranges = [(int(u), int(u) + 40) for u in np.linspace(1, n - 40, 7)]
     keys = ("px", "py", "qx", "qy", "len", "element")
     results = []
-    for pipeline in (0, 1, 2):
+    for pipeline in (0, 1, 2, 3):
         tg.set_option("pipeline", pipeline)
-        chk, slices = [], {}
+        chk, slices, sums = [], {}, {}
 
-        def on_batch(b, chk=chk, slices=slices):
+        def on_batch(b, chk=chk, slices=slices, sums=sums):
             torch.cuda.synchronize()
             cols = {k: torch.as_tensor(getattr(b, k), device="cuda") for k in keys}
             off = torch.as_tensor(api.DeviceColumn(b.d_offsets, n + 1, "<i8"), device="cuda")
@@ -416,10 +418,11 @@ def test_cfg4_full_size_pipelines_agree():
             step = 1 << 27
             for lo in range(0, b.n_segments, step):
                 hi = min(b.n_segments, lo + step)
-                w = torch.arange(lo, hi, device="cuda", dtype=torch.int64) % 1021 + 1  # position-dependent weights
-                row.append(int((cols["element"][lo:hi].to(torch.int64) * w).sum()))
+                # weights from the GLOBAL segment position: the sums do not depend on how a pipeline cuts the batches
+                w = (torch.arange(lo, hi, device="cuda", dtype=torch.int64) + int(b.offset_base)) % 1021 + 1
+                sums["element"] = sums.get("element", 0) + int((cols["element"][lo:hi].to(torch.int64) * w).sum())
                 for k in keys[:5]:  # bit patterns, so that any differing bit changes the sum
-                    row.append(int((cols[k][lo:hi].view(torch.int64) & 0xFFFFFFFF).mul_(w).sum()))
+                    sums[k] = sums.get(k, 0) + int((cols[k][lo:hi].view(torch.int64) & 0xFFFFFFFF).mul_(w).sum())
             chk.append(tuple(row))
             for (u0, u1) in ranges:
                 if b.uid_begin <= u0 and u1 <= b.uid_end:
@@ -432,7 +435,8 @@ def test_cfg4_full_size_pipelines_agree():
         assert tg.n_segments > 7_000_000_000 and len(chk) >= 4
         assert sum(r[2] for r in chk) == tg.n_segments
         assert math.isclose(tg.volumes.sum(), area, rel_tol=1e-8)
-        results.append((tg.n_segments, chk, tg.segment_offsets.copy(), tg.segment_status.copy(), slices))
+        assert [r[0] for r in chk[1:]] == [r[1] for r in chk[:-1]] and chk[0][0] == 1 and chk[-1][1] == n + 1  # batches tile the uids
+        results.append((tg.n_segments, sums, tg.segment_offsets.copy(), tg.segment_status.copy(), slices))
     for other in results[1:]:
         assert other[0] == results[0][0] and other[1] == results[0][1]
         assert np.array_equal(other[2], results[0][2]) and np.array_equal(other[3], results[0][3])
@@ -478,7 +482,7 @@ def test_two_stage_pipeline_falls_back_to_sequential(pincell_model):
     rt.trace_(tg)
     rt.segmentize_(tg, check=False)
     assert_segments_equal(otg, tg)
-    for pipeline in (0, 2):
+    for pipeline in (0, 2, 3):
         tg.set_option("pipeline", pipeline)
         tg.set_option("debug_verify_fail", 0)
         rt.segmentize_(tg, check=False)
@@ -494,3 +498,49 @@ def test_two_stage_pipeline_falls_back_to_sequential(pincell_model):
     rt.segmentize_(tg, check=False)
     assert tg.info("verify_fallbacks") == 0 and tg.info("eval_ms") == 0
     assert_segments_equal(otg, tg)
+
+
+def test_single_walk_pipeline_batches_and_pool_exhaustion():
+    """pipeline 3 (k_topo<2> + k_eval3): uid batches of the count walk when the record pool is small, sub-batches of the
+    evaluation when the Segment columns are small, chunks longer than one pool block, and the fall-back to the hybrid pipeline
+    when the pool runs out -- always the oracle's bits."""
+    model = rt.synth.jittered_triangle_mesh(130, 130, seed=21)
+    mesh = rt.Mesh(model)
+    otg = OracleTrackGenerator(OracleMesh.from_mesh(mesh), 16, 0.004).trace().segmentize(check=False, nthreads=8)
+    tg = rt.TrackGenerator(mesh, 16, 0.004)
+    rt.trace_(tg)
+    tg.set_option("pipeline", 3)
+    tg.set_option("chunk_segments", 700)  # one walker per track: up to ~370 segments = two pool blocks (walk.cuh kRecBlock = 256)
+    rt.segmentize_(tg, check=False)
+    assert tg.info("verify_fallbacks") == 0 and tg.info("count_batches") == 1
+    assert_segments_equal(otg, tg)
+    assert_volumes_close(otg, tg)
+    off_all = tg.segment_offsets.copy()
+    tg.set_option("chunk_segments", 40)
+    tg.set_option("pool_slots", 2048)  # many count batches
+    rt.segmentize_(tg, check=False)
+    assert tg.info("verify_fallbacks") == 0 and tg.info("count_batches") > 3
+    assert np.array_equal(tg.segment_offsets, off_all) and tg.n_segments == otg.n_segments
+    s = tg.segments  # the last count batch is resident
+    n = s["px"].shape[0]
+    assert 0 < n < otg.n_segments
+    for key in ("px", "py", "qx", "qy", "len", "element"):
+        assert np.array_equal(s[key], otg.seg[key][-n:])
+    assert_volumes_close(otg, tg)
+    from raytracing_jl_b200 import _lib as L
+    L.check(tg._ctx, L.lib().rt_set_segment_capacity(tg._ctx, 5000))  # ... and evaluation sub-batches inside each of them
+    rt.segmentize_(tg, check=False)
+    assert tg.info("verify_fallbacks") == 0 and np.array_equal(tg.segment_offsets, off_all)
+    n = tg.segments["px"].shape[0]
+    assert 0 < n <= 5000
+    for key in ("px", "py", "qx", "qy", "len", "element"):
+        assert np.array_equal(tg.segments[key], otg.seg[key][-n:])
+    assert_volumes_close(otg, tg)
+    L.check(tg._ctx, L.lib().rt_set_segment_capacity(tg._ctx, 0))
+    tg.set_option("pool_slots", 0)
+    tg.set_option("pool_extra", 0)  # no spare blocks: chunks longer than one block exhaust the pool
+    tg.set_option("chunk_segments", 700)
+    rt.segmentize_(tg, check=False)
+    assert tg.info("verify_fallbacks") == 1
+    assert_segments_equal(otg, tg)
+    assert_volumes_close(otg, tg)
