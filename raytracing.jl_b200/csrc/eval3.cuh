@@ -53,31 +53,36 @@ __global__ void __launch_bounds__(kEval3Threads, RT_EVAL3_MIN_BLOCKS) k_eval3(co
     if (slot >= P.unit_end) return;
     const int ls = (int)(w & 31);
     const long long unit = P.ch.order ? P.ch.order[slot] : slot;
+    // Everything that only needs the chunk slot is requested at once, BEFORE the early exits (a warp lives for ~4 iterations,
+    // so a chain of dependent header loads in front of them costs as much as the arithmetic): count, first records, prefix,
+    // seed point next to the unit's block; then the track's data; then the per-angle data.
+    const long long cidx = unit * 32 + ls;
+    const int pb0 = (int)(cidx - P.pool_slot_base);
+    int pb = pb0;
+    const int cnt = P.ch.count[cidx];
+    const int rec_first = P.pool[(long long)pb * kRecBlock + lane];
+    const int prefix = P.ch.prefix[cidx];
+    const double seedx = P.ch.seed_qx[cidx], seedy = P.ch.seed_qy[cidx];
     const int blk = P.ch.unit_block[unit];
     const long long t = 32LL * blk + ls;
     if (t >= P.n_tracks || t < P.trk_begin || t >= P.trk_end) return;
-    const int j = (int)(unit - P.ch.unit_base[blk]);
-    if (j >= P.ch.nch[t]) return;
-    const long long cidx = unit * 32 + ls;
-    const int cnt = P.ch.count[cidx];
-    if (cnt <= 0) return;
-    const int pb0 = (int)(cidx - P.pool_slot_base);
-    int pb = pb0;
-    int rec = lane < cnt ? P.pool[(long long)pb * kRecBlock + lane] : 1;  // (in flight while the track is fetched)
-
-    const unsigned long long pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
+    const int nch = P.ch.nch[t];
+    const long long ubase = P.ch.unit_base[blk];
     const int az = P.t.azim[t];
     const Line trk{P.t.a[t], P.t.b[t], P.t.c[t]};
+    const long long off_t = P.offsets[t];
+    const int j = (int)(unit - ubase);
+    if (j >= nch) return;  // (count is only defined for the chunks the track has)
+    if (cnt <= 0) return;
+    int rec = lane < cnt ? rec_first : 1;
+
+    const unsigned long long pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
     const bool right = P.ang.phi[az] < kPi / 2;  // isless(phi, pi/2), src/intersection.jl:153
     const double delta = P.vol ? P.ang.delta_eff[az] : 0.0;
-    const long long base = P.offsets[t] - P.offset_base + P.ch.prefix[cidx];
+    const long long base = off_t - P.offset_base + prefix;
     // entry point of the chunk's first segment when that is a fast record: the exit point of the seed cell (k_seed), which
     // the previous chunk's walker pushed last.  Afterwards: q of the previous iteration's lane 31 (kept in lane 0).
-    double cqx = 0.0, cqy = 0.0;
-    if (j > 0) {
-        cqx = P.ch.seed_qx[cidx];
-        cqy = P.ch.seed_qy[cidx];
-    }
+    double cqx = seedx, cqy = seedy;  // (only used when j > 0)
     int cfast = j > 0;
     double lsum = 0.0;
     bool bad = false, any_lit = false;
