@@ -178,13 +178,13 @@ def workload_config(args, model, n_azim, delta):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="cfg3")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--clock-period-ms", type=float, default=10.0)
+    ap.add_argument("--clock-period-ms", type=float, default=20.0)
     ap.add_argument("--pipeline", type=int, default=None, help="rt_set_option('pipeline'): 0 hybrid, 1 sequential, 2 two-stage, 3 single-walk")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -225,17 +225,27 @@ def main():
 
     for _ in range(args.warmup):
         step()
-    sampler = ClockSampler(local, period=args.clock_period_ms * 1e-3)
-    sampler.start()
-    barrier()
-    tg.timer_start()
-    phases = []
-    for _ in range(args.steps):
-        step()
-        phases.append(tg.phase_ms())
-    ms = tg.timer_stop()
-    barrier()
-    clocks = sampler.stop()
+    retimed = False
+    for attempt in range(2):
+        sampler = ClockSampler(local, period=args.clock_period_ms * 1e-3)
+        sampler.start()
+        barrier()
+        tg.timer_start()
+        phases = []
+        for _ in range(args.steps):
+            step()
+            phases.append(tg.phase_ms())
+        ms = tg.timer_stop()
+        barrier()
+        clocks = sampler.stop()
+        # The timed region is device time between two events on the library's stream, host gaps included.  A region that took
+        # more than twice its own kernel phases was disturbed on the host side (another process, a driver hiccup on a fresh box):
+        # it is re-measured once, and the JSON line says so.
+        kern = float(np.sum([sum(p[k] for k in ("count", "scan", "fill", "volumes")) for p in phases]))
+        if attempt == 0 and world == 1 and ms > 2.0 * kern + 1.0:
+            retimed = True
+            continue
+        break
     nseg_local = tg.n_segments
     st = tg.stats()
     if world > 1:
@@ -312,7 +322,7 @@ def main():
                "gpu_launches": int(st["launches"] + 1) * args.steps,
                "phase_ms": {k: float(np.mean([p[k] for p in phases])) for k in phases[0]},
                "walk_stats": {k: st[k] for k in ("fast_transitions", "literal_iterations", "nn_queries", "knn_queries")},
-               "bad_tracks_status": int(tg.bad_status)}
+               "bad_tracks_status": int(tg.bad_status), "retimed": retimed, "verify_fallbacks": int(tg.info("verify_fallbacks"))}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
