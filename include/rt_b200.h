@@ -177,6 +177,18 @@ int rt_quadrature_device(rt_ctx *ctx, rt_quad_view *view, double *omega_host);
 int rt_optical_lengths(rt_ctx *ctx, int32_t n_groups, const double *sigma_t, int32_t layout, const double **d_tau,
                        double *tau_host);
 
+/* ---- exact element volumes and the volume correction -------------------------------------
+ * rt_element_volumes: element_volume(mesh, node_ids) = 1/2*abs((x2-x1) x (x3-x1)) for every cell (src/trackgenerator.jl:402-411),
+ * computed on the device; `areas` (n_cells, may be NULL) receives a copy, *d_areas (may be NULL) the device buffer.
+ * rt_correct_volumes: the step the reference only announces ("correct volumes by changing segment lengths",
+ * src/trackgenerator.jl:388-397, flag `volume_correction` :48): after rt_segmentize + rt_volumes, every resident segment length
+ * is multiplied by factor[element] = area[element] / volumes[element] (1 where no track crosses the element), so that the
+ * traced volumes of the corrected lengths equal the exact areas.  p and q are left untouched.  `factors` / *d_factors: the
+ * n_cells factors (host copy / device buffer; either may be NULL).  With batched segments call it from the batch callback of
+ * a SECOND rt_segmentize (the factors need the volumes of all tracks). */
+int rt_element_volumes(rt_ctx *ctx, double *areas, const double **d_areas);
+int rt_correct_volumes(rt_ctx *ctx, double *factors, const double **d_factors);
+
 /* ---- volumes: replaces the tail of fill_volumes (src/trackgenerator.jl:378-386) -----------------------
  * volumes[e] = (sum over this context's segments of delta_eff[azim]*len) / n_azim_2, after an NCCL
  * all-reduce across the communicator set up with rt_comm_init (skipped when there is none). */
@@ -192,8 +204,9 @@ int rt_comm_init(rt_ctx *ctx, int32_t n_ranks, int32_t rank, const char id[128])
  * stats[0..7] of the last rt_segmentize: kernel launches, fast transitions, slow (literal) iterations,
  * nearest-node queries, knn queries, count-pass ms, fill-pass ms, scan+volumes ms. */
 int rt_stats(rt_ctx *ctx, double stats[8]);
-/* named scalars: "verify_fallbacks", "eval_ms" (stage 2 of the two-stage fill), "n_units", "segment_capacity" of the last
- * rt_segmentize; "tau_ms" (k_tau alone) of the last rt_optical_lengths */
+/* named scalars: "verify_fallbacks", "eval_ms" (stage 2 of the two-stage fill), "n_units", "segment_capacity", "count_batches"
+ * (uid batches of the single-walk pipeline's count walk) of the last rt_segmentize; "tau_ms" (k_tau alone) of the last
+ * rt_optical_lengths */
 int rt_info(rt_ctx *ctx, const char *key, double *value);
 /* CUDA-event time (ms) of the last call's device work, by phase: 0 upload+prep, 1 trace, 2 count,
  * 3 scan, 4 fill, 5 volumes(+allreduce) */
@@ -203,11 +216,14 @@ int rt_phase_ms(rt_ctx *ctx, double ms[6]);
  * mantissas) through the shared-reciprocal division the walk kernels use, compared bit for bit with the IEEE `/`. */
 int rt_selftest_division(rt_ctx *ctx, int64_t n_threads, uint64_t seed, int32_t exp_span, int64_t *mismatches);
 
-/* tuning knobs: "chunk_segments" (minimum expected segments per sub-track chunk, default 64),
+/* tuning knobs: "chunk_segments" (minimum expected segments per sub-track chunk, default 128),
  * "target_walkers" (chunks are sized so that about this many walkers exist, default 148*2048*4),
- * "order_grid" (G: walkers are launched in Morton order of a G x G tiling of the domain, default 16, 0 = uid order),
- * "pipeline" (0: sign-test count walk + geometric fill walk [default], 1: sequential walks only, 2: sign-test walks + one
- * thread per segment; 0 and 2 verify themselves and restart in mode 1 on any disagreement) */
+ * "order_grid" (G: walkers are launched in Morton order of a G x G tiling of the domain, default 32, 0 = uid order),
+ * "pipeline" (3: ONE sign-test walk that counts and records every chunk + one lane per segment [default]; 0: sign-test count
+ * walk + geometric fill walk; 1: sequential geometric walks only; 2: sign-test count walk + sign-test record walk + one thread
+ * per segment.  0, 2 and 3 verify themselves and restart in mode 1 on any disagreement; 3 restarts in mode 0 when its record
+ * pool runs out), "march" (0: k_topo<2> instead of k_march in pipeline 3), "pool_slots" / "pool_extra" (test hooks: chunk slots
+ * per count batch, spare record blocks), "eval_waves", "debug_verify_fail" (test hook) */
 int rt_set_option(rt_ctx *ctx, const char *name, double value);
 /* CUDA-event stopwatch on the context's launching stream (bench harness: torch.cuda.Event cannot see it). */
 int rt_timer_start(rt_ctx *ctx);

@@ -166,6 +166,24 @@ function b200_optical_lengths!(t::TrackGenerator{T}, Σt::Matrix{Float64}) where
 end
 
 """
+    b200_correct_volumes!(t::TrackGenerator) -> Vector{Float64}
+
+What `fill_volumes` announces but leaves as a TODO (src/trackgenerator.jl:388-397): every `segment.ℓ` of element `e` is scaled by
+`element_volume(e) / t.volumes[e]` on the device (include/rt_b200.h: rt_correct_volumes), so that the traced volumes of the
+corrected lengths equal the exact cell areas.  Returns the per-element factors; call it after `segmentize!` when
+`t.volume_correction` is set.  (`Segment` is immutable: the corrected lengths are read back into fresh `Segment`s.)
+"""
+function b200_correct_volumes!(t::TrackGenerator{T}) where {T}
+    ctx = _b200_context(t)
+    factors = Vector{Float64}(undef, num_cells(t.mesh.model))
+    _b200_check(ctx, ccall((:rt_correct_volumes, LIBRT_B200), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Ptr{Float64}}), ctx, factors, C_NULL))
+    for track in t.tracks_by_uid, (i, s) in enumerate(track.segments)
+        track.segments[i] = Segment{T}(s.p, s.q, s.ℓ * factors[s.element], s.τ, s.element)
+    end
+    return factors
+end
+
+"""
     b200_mesh_upload_device_ingest(ctx, model)
 
 Mesh ingestion at scale: only node coordinates and the cell→node table cross the ABI; the vertex→cells table

@@ -458,6 +458,20 @@ class TrackGenerator(TrackLayout):
         _lib.check(self._ctx, _lib.lib().rt_optical_lengths(self._ctx, G, sig.reshape(-1), int(layout), C.byref(d), _lib.ptr(host)))
         return host, DeviceColumn(d.value, n * G, "<f8")
 
+    def element_volumes(self):
+        """element_volume of every cell (src/trackgenerator.jl:402-411: the `volumes2` the reference computes and discards)."""
+        a = np.zeros(self.mesh.num_cells)
+        _lib.check(self._ctx, _lib.lib().rt_element_volumes(self._ctx, _lib.ptr(a), None))
+        return a
+
+    def correct_volumes(self):
+        """The reference's announced volume correction (src/trackgenerator.jl:388): resident segment lengths are scaled by
+        area[element] / volumes[element].  Returns the per-element factors; ``tg.segments`` is re-read afterwards."""
+        f = np.zeros(self.mesh.num_cells)
+        _lib.check(self._ctx, _lib.lib().rt_correct_volumes(self._ctx, _lib.ptr(f), None))
+        self._segments = None
+        return f
+
     def phase_ms(self):
         ms = np.zeros(6)
         _lib.lib().rt_phase_ms(self._ctx, ms)
@@ -612,4 +626,7 @@ def segmentize_(tg: TrackGenerator, k: int = 5, rtol: float = RTOL_DEFAULT, flag
         tg._segmented = True
     if not (flags & _lib.RT_SEG_NO_VOLUMES):
         _lib.check(tg._ctx, L.rt_volumes(tg._ctx, _lib.ptr(tg.volumes) if fetch_volumes else None))
+        # volume_correction = true: the reference's TODO (src/trackgenerator.jl:388), applied when every segment is resident
+        if tg.volume_correction and on_batch is None and not (flags & _lib.RT_SEG_COUNT_ONLY) and tg.info("segment_capacity") >= tg.n_segments:
+            tg.volume_factors = tg.correct_volumes()
     return tg

@@ -81,6 +81,8 @@ struct rt_ctx {
     DevBuf b_order, b_okeys, b_ohist;  // spatial execution order of the units
     DevBuf b_evalblk, b_trkrec;
     DevBuf b_omega, b_sigma, b_tau;  // sweep-facing exports (sweep.cuh)
+    DevBuf b_area, b_factor;         // exact element volumes, volume-correction factors (sweep.cuh)
+    bool area_valid = false;
     long long *h_pin = nullptr;  // page-locked scratch for the small device->host read-backs of rt_segmentize (16 words)
     DevBuf b_scratch, b_gcounts, b_gcursor;  // rt_mesh_upload staging (kept between uploads)
     DevBuf b_rec, b_verify, b_tsum;    // two-stage pipeline: per-segment records, verification flag, per-track length sums
@@ -216,7 +218,8 @@ extern "C" void rt_destroy(rt_ctx *ctx) {
                      &ctx->b_order,   &ctx->b_okeys,      &ctx->b_ohist,     &ctx->b_rec,     &ctx->b_verify,    &ctx->b_tsum,      &ctx->b_evalblk,   &ctx->b_trkrec,
                      &ctx->b_scratch, &ctx->b_gcounts,   &ctx->b_gcursor,
                      &ctx->b_omega,   &ctx->b_sigma,     &ctx->b_tau,
-                     &ctx->b_pool,    &ctx->b_pool_next, &ctx->b_pool_cursor};
+                     &ctx->b_pool,    &ctx->b_pool_next, &ctx->b_pool_cursor,
+                     &ctx->b_area,    &ctx->b_factor};
     for (DevBuf *b : all) release(*b);
     for (int ph = 0; ph < 6; ++ph)
         for (int q = 0; q < 2; ++q)
@@ -386,6 +389,7 @@ extern "C" int rt_mesh_upload(rt_ctx *ctx, int32_t n_nodes, const double *xy, in
     ctx->area = sc.area;
     ctx->clear_tiny = -1.0;
     ctx->has_mesh = true;
+    ctx->area_valid = false;
     ctx->traced = false;
     ctx->segmented = false;
     return RT_OK;
@@ -800,7 +804,13 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
     long long base = 0;  // segments of the batches already done
     long long B0 = 0;
     ctx->count_batches = 0;
-    ctx->phase_ms[4] = 0.0;
+    // phase times are accumulated over the batches (every batch ends with a stream synchronisation anyway)
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    auto take = [&](int ph) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->pev[ph][0], ctx->pev[ph][1]) == cudaSuccess) acc[ph] += (double)ms;
+        ctx->pev_dirty[ph] = false;
+    };
     while (B0 < n_blocks) {
         long long B1 = n_blocks;
         if (multi) {
@@ -824,6 +834,7 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
         ctx->h_pin[8] = 0;
         *(int *)&ctx->h_pin[8] = (int)slots;
         CK(cudaMemcpyAsync(P.pool_cursor, &ctx->h_pin[8], sizeof(int), cudaMemcpyHostToDevice, st));
+        if (B0 > 0) tic(ctx, 2);  // (the first batch's count phase started with the chunk plan)
         k_seed<<<blocks_for(slots, 128), 128, 0, st>>>(P);
         if (ctx->opt_march)
             k_march<<<blocks_for(slots, kMarchThreads), kMarchThreads, 0, st>>>(P);
@@ -831,14 +842,16 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
             k_topo<2><<<blocks_for(slots, kTopoThreads), kTopoThreads, 0, st>>>(P);
         k_fixup_tracks<<<blocks_for(e - b, 128), 128, 0, st>>>(P);
         CK(cudaGetLastError());
-        if (B0 == 0) toc(ctx, 2);
-        if (B0 == 0) tic(ctx, 3);
+        toc(ctx, 2);
+        tic(ctx, 3);
         CK((exclusive_scan<int, long long>(ctx, (const int *)ctx->b_count.p + b, (long long *)ctx->b_offsets.p + b, e - b, base)));
-        if (B0 == 0) toc(ctx, 3);
+        toc(ctx, 3);
         launches += 6;
         CK(cudaMemcpyAsync(&ctx->h_pin[1], (long long *)ctx->b_offsets.p + e, sizeof(long long), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&ctx->h_pin[9], P.pool_cursor, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        take(2);
+        take(3);
         const long long batch_total = ctx->h_pin[1] - base;
         if ((long long)*(int *)&ctx->h_pin[9] > (long long)P.pool_blocks) {  // some walker found the pool empty
             *next_mode = 0;
@@ -882,7 +895,6 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
             CK(cudaMemcpyAsync(h_off.data(), (long long *)ctx->b_offsets.p + b, sizeof(long long) * h_off.size(), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
         }
-        if (B0 == 0) tic(ctx, 4);
         long long sb = b;
         while (sb < e) {
             long long se = e;
@@ -903,6 +915,7 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
             }
             WalkParams PE = P;
             PE.lmin = lmin_eval;
+            tic(ctx, 4);
             if (nseg_b > 0)
                 k_eval3<<<blocks_for((PE.unit_end - PE.unit_begin) * 32 * 32, kEval3Threads), kEval3Threads, 0, st>>>(PE);
             E.trk_begin = sb;
@@ -916,10 +929,11 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
             ctx->res_trk_end = se;
             ctx->res_off_base = off_b;
             ctx->res_nseg = nseg_b;
-            if (B0 == 0 && se == e) toc(ctx, 4);
+            toc(ctx, 4);
             ctx->h_pin[2] = 0;
             CK(cudaMemcpyAsync(&ctx->h_pin[2], ctx->b_verify.p, sizeof(int), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
+            take(4);
             if ((int)ctx->h_pin[2]) {
                 *verify_failed = true;
                 return RT_OK;
@@ -936,6 +950,7 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
         base += batch_total;
         B0 = B1;
     }
+    for (int ph = 2; ph <= 4; ++ph) ctx->phase_ms[ph] = acc[ph];
     *launches_io += launches;
     return RT_OK;
 }
@@ -1459,6 +1474,49 @@ extern "C" int rt_optical_lengths(rt_ctx *ctx, int32_t n_groups, const double *s
     cudaEventElapsedTime(&ms, ctx->ev2[0], ctx->ev2[1]);
     ctx->tau_ms = ms;
     if (d_tau) *d_tau = (const double *)ctx->b_tau.p;
+    return RT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// exact element volumes and the volume correction
+// ------------------------------------------------------------------------------------------------------
+static int ensure_areas(rt_ctx *ctx) {
+    if (ctx->area_valid) return RT_OK;
+    const int nc = ctx->m.n_cells;
+    CK(ensure(ctx->b_area, sizeof(double) * (size_t)nc));
+    k_element_volumes<<<blocks_for(nc, 256), 256, 0, ctx->stream>>>(nc, ctx->m.cell_nodes, ctx->m.xy, (double *)ctx->b_area.p);
+    CK(cudaGetLastError());
+    ctx->area_valid = true;
+    return RT_OK;
+}
+
+extern "C" int rt_element_volumes(rt_ctx *ctx, double *areas, const double **d_areas) {
+    if (!ctx || !ctx->has_mesh) return fail(ctx, RT_ERR_ARG, "rt_element_volumes: upload a mesh first");
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_areas(ctx);
+    if (rc) return rc;
+    if (areas) CK(cudaMemcpyAsync(areas, ctx->b_area.p, sizeof(double) * (size_t)ctx->m.n_cells, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (d_areas) *d_areas = (const double *)ctx->b_area.p;
+    return RT_OK;
+}
+
+extern "C" int rt_correct_volumes(rt_ctx *ctx, double *factors, const double **d_factors) {
+    if (!ctx || !ctx->segmented || !ctx->vol_valid || !ctx->b_voln.p)
+        return fail(ctx, RT_ERR_ARG, "rt_correct_volumes: run rt_segmentize with volumes enabled and rt_volumes first");
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_areas(ctx);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    const int nc = ctx->m.n_cells;
+    CK(ensure(ctx->b_factor, sizeof(double) * (size_t)nc));
+    k_volume_factors<<<blocks_for(nc, 256), 256, 0, st>>>(nc, (const double *)ctx->b_area.p, (const double *)ctx->b_voln.p, (double *)ctx->b_factor.p);
+    if (ctx->res_nseg > 0)
+        k_scale_lengths<<<blocks_for(ctx->res_nseg, 256), 256, 0, st>>>(ctx->res_nseg, ctx->s_elem, (const double *)ctx->b_factor.p, ctx->s_len);
+    CK(cudaGetLastError());
+    if (factors) CK(cudaMemcpyAsync(factors, ctx->b_factor.p, sizeof(double) * (size_t)nc, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (d_factors) *d_factors = (const double *)ctx->b_factor.p;
     return RT_OK;
 }
 

@@ -44,4 +44,30 @@ __global__ void k_tau(long long n_seg, int n_groups, const double *__restrict__ 
     tau[i] = sigma_t[(long long)e * n_groups + g] * len[s];
 }
 
+// element_volume(mesh, node_ids) = 1/2 * abs((x2 - x1) x (x3 - x1))  (src/trackgenerator.jl:402-411): the exact cell areas the
+// reference computes into `volumes2` and then discards (its volume correction is a TODO, src/trackgenerator.jl:388-397).
+// Gridap's cross of two 2-vectors: a[1]*b[2] - a[2]*b[1].
+__global__ void k_element_volumes(int n_cells, const int *__restrict__ cell_nodes, const double2 *__restrict__ xy, double *__restrict__ area) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    const double2 x1 = xy[cell_nodes[3 * c]], x2 = xy[cell_nodes[3 * c + 1]], x3 = xy[cell_nodes[3 * c + 2]];
+    const double ax = x2.x - x1.x, ay = x2.y - x1.y, bx = x3.x - x1.x, by = x3.y - x1.y;
+    area[c] = 0.5 * fabs(ax * by - ay * bx);
+}
+
+// The correction the reference announces ("correct volumes by changing segment lengths", src/trackgenerator.jl:388): every
+// segment length of element e is scaled by area[e] / traced_volume[e], so that the traced volumes (src/trackgenerator.jl:371-386)
+// of the corrected segments equal the exact areas.  Elements no track crosses (traced volume 0) keep factor 1.
+__global__ void k_volume_factors(int n_cells, const double *__restrict__ area, const double *__restrict__ vol, double *__restrict__ factor) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    const double v = vol[c];
+    factor[c] = v > 0.0 ? area[c] / v : 1.0;
+}
+__global__ void k_scale_lengths(long long n_seg, const int *__restrict__ element, const double *__restrict__ factor, double *__restrict__ len) {
+    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    len[s] = len[s] * factor[element[s] - 1];
+}
+
 }  // namespace rt

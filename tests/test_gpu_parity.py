@@ -544,3 +544,35 @@ def test_single_walk_pipeline_batches_and_pool_exhaustion():
     assert tg.info("verify_fallbacks") == 1
     assert_segments_equal(otg, tg)
     assert_volumes_close(otg, tg)
+
+
+def test_element_volumes_and_volume_correction(pincell_model):
+    """element_volume (src/trackgenerator.jl:402-411) on the device, bit-equal to the reference's formula, and the
+    volume correction the reference only announces (:388-397): lengths scaled by area/volume per element, after which the
+    traced volumes (src/trackgenerator.jl:371-386) of the corrected segments equal the exact areas."""
+    for model, n_azim, delta in ((pincell_model, 8, 0.02), (rt.synth.jittered_triangle_mesh(40, 33, 2.0, 1.5, 0.3, 17, x0=-1.0, y0=4.0), 16, 0.01)):
+        tg = rt.TrackGenerator(model, n_azim, delta, volume_correction=True)
+        xy = np.asarray(model.node_coordinates, dtype=np.float64).reshape(-1, 2)
+        tri = model.triangles0()
+        x1, x2, x3 = xy[tri[:, 0]], xy[tri[:, 1]], xy[tri[:, 2]]
+        ax, ay, bx, by = x2[:, 0] - x1[:, 0], x2[:, 1] - x1[:, 1], x3[:, 0] - x1[:, 0], x3[:, 1] - x1[:, 1]
+        area = 1 / 2 * np.abs(ax * by - ay * bx)  # 1 / 2 * abs((x2 - x1) x (x3 - x1))
+        assert np.array_equal(tg.element_volumes(), area)
+        assert math.isclose(area.sum(), rt.synth.mesh_area(model), rel_tol=1e-12)
+        rt.trace_(tg)
+        tg.volume_correction = False
+        rt.segmentize_(tg)
+        raw = {k: v.copy() for k, v in tg.segments.items()}
+        vol = tg.volumes.copy()
+        tg.volume_correction = True
+        rt.segmentize_(tg)
+        f = tg.volume_factors
+        assert np.array_equal(f, np.where(vol > 0, area / np.where(vol > 0, vol, 1.0), 1.0))
+        s = tg.segments
+        e = raw["element"] - 1
+        assert np.array_equal(s["len"], raw["len"] * f[e])  # lengths scaled ...
+        assert all(np.array_equal(s[k], raw[k]) for k in ("px", "py", "qx", "qy", "element"))  # ... end points untouched
+        azim = np.repeat(np.array([t.azim_idx for t in tg.tracks_by_uid]) - 1, np.diff(tg.segment_offsets))
+        traced = np.bincount(e, weights=tg.azimuthal_quadrature.deltas[azim] * s["len"], minlength=area.size) / (n_azim // 2)
+        crossed = vol > 0
+        assert crossed.mean() > 0.99 and np.allclose(traced[crossed], area[crossed], rtol=1e-12, atol=0.0)
