@@ -191,6 +191,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly ONE JSON line: anything a library prints there meanwhile (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -323,7 +328,10 @@ def main():
                "phase_ms": {k: float(np.mean([p[k] for p in phases])) for k in phases[0]},
                "walk_stats": {k: st[k] for k in ("fast_transitions", "literal_iterations", "nn_queries", "knn_queries")},
                "bad_tracks_status": int(tg.bad_status), "retimed": retimed, "verify_fallbacks": int(tg.info("verify_fallbacks"))}
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

@@ -23,9 +23,12 @@
 
 namespace rt {
 
-constexpr int kEval3Threads = 256;
+#ifndef RT_EVAL3_THREADS
+#define RT_EVAL3_THREADS 128
+#endif
+constexpr int kEval3Threads = RT_EVAL3_THREADS;
 #ifndef RT_EVAL3_MIN_BLOCKS
-#define RT_EVAL3_MIN_BLOCKS 4
+#define RT_EVAL3_MIN_BLOCKS 8
 #endif
 
 // intersection(track, L) (src/intersection.jl:127-138) through the shared-reciprocal division; `redo` is set when a quotient did

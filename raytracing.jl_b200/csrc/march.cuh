@@ -16,7 +16,10 @@
 
 namespace rt {
 
-constexpr int kMarchThreads = 128;
+#ifndef RT_MARCH_THREADS
+#define RT_MARCH_THREADS 128
+#endif
+constexpr int kMarchThreads = RT_MARCH_THREADS;
 #ifndef RT_MARCH_WAIT
 #define RT_MARCH_WAIT 6
 #endif

@@ -1309,8 +1309,8 @@ extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rt
         ctx->clear_tiny = tiny_step;
     }
     if (want_vol) {
+        // (pageable source: the call returns once the n2 values are staged, no synchronisation needed before the caller reuses them)
         CK(cudaMemcpyAsync((double *)ctx->b_ang_d.p + 6 * (size_t)n2, delta_eff, sizeof(double) * n2, cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));
         ctx->has_delta = true;
         CK(ensure(ctx->b_vol, sizeof(double) * (size_t)m.n_cells));
     }
