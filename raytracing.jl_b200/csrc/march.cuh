@@ -247,7 +247,7 @@ __device__ __noinline__ void march_init(const WalkParams &P, MarchState &s, int 
     const int seed = s.j == 0 ? -2 : P.ch.seed_cell[s.cidx];
     if (seed == -1) return;  // void seed: the previous walker continues through this chunk (count 0, END_HANDOFF)
     s.active = 1;
-    constexpr double kKappa = 1.0 / 64.0;
+    constexpr double kKappa = 1.0 / RT_KAPPA_INV;
     s.az = P.t.azim[t];
     s.ta = P.t.a[t];
     s.tb = P.t.b[t];

@@ -77,6 +77,7 @@ struct rt_ctx {
     // segmentation
     bool segmented = false;
     DevBuf b_count, b_status, b_offsets, b_tile, b_vol, b_voln, b_counters, b_bad;
+    DevBuf b_layout;  // per-track chunk layout (walk.cuh ChunkLayout)
     DevBuf b_nch, b_blk_chunks, b_unit_base, b_unit_block, b_ch_i, b_ch_d;  // chunk plan (walk.cuh ChunkPlan)
     DevBuf b_order, b_okeys, b_ohist;  // spatial execution order of the units
     DevBuf b_evalblk, b_trkrec;
@@ -88,6 +89,7 @@ struct rt_ctx {
     DevBuf b_rec, b_verify, b_tsum;    // two-stage pipeline: per-segment records, verification flag, per-track length sums
     DevBuf b_pool, b_pool_next, b_pool_cursor;  // single-walk pipeline: record blocks (walk.cuh kRecBlock), chain, cursor
     int count_batches = 0;             // single-walk pipeline: how many uid batches the count walk needed (info)
+    int opt_band_chunks = 1;           // 8x shorter chunks for tracks that run along the bounding box (walk.cuh k_plan_chunks)
     int opt_march = 1;                 // single-walk pipeline: k_march (register-resident loop) instead of k_topo<2>
     long long opt_pool_slots = 0;      // test hook: at most this many chunk slots per count batch (0: as many as fit)
     double opt_pool_extra = 1.25;      // spare pool blocks, as a multiple of (expected segments / kRecBlock)
@@ -219,7 +221,7 @@ extern "C" void rt_destroy(rt_ctx *ctx) {
                      &ctx->b_scratch, &ctx->b_gcounts,   &ctx->b_gcursor,
                      &ctx->b_omega,   &ctx->b_sigma,     &ctx->b_tau,
                      &ctx->b_pool,    &ctx->b_pool_next, &ctx->b_pool_cursor,
-                     &ctx->b_area,    &ctx->b_factor};
+                     &ctx->b_area,    &ctx->b_factor,    &ctx->b_layout};
     for (DevBuf *b : all) release(*b);
     for (int ph = 0; ph < 6; ++ph)
         for (int q = 0; q < 2; ++q)
@@ -1022,8 +1024,11 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         CK(ensure(ctx->b_nch, sizeof(int) * (size_t)n));
         CK(ensure(ctx->b_blk_chunks, sizeof(int) * (size_t)n_blocks));
         CK(ensure(ctx->b_unit_base, sizeof(long long) * ((size_t)n_blocks + 1)));
-        k_plan_chunks<<<blocks_for(n_blocks * 32, 128), 128, 0, st>>>(n, ctx->t.len, chunk_len, (int *)ctx->b_nch.p,
-                                                                     (int *)ctx->b_blk_chunks.p);
+        PlanGeom pg{ctx->t.px, ctx->t.py, ctx->t.qx, ctx->t.qy, {m.bbmin[0], m.bbmin[1]}, {m.bbmax[0], m.bbmax[1]},
+                    ctx->opt_band_chunks ? ctx->lmax : 0.0};
+        CK(ensure(ctx->b_layout, sizeof(ChunkLayout) * (size_t)n));
+        k_plan_chunks<<<blocks_for(n_blocks * 32, 128), 128, 0, st>>>(n, ctx->t.len, chunk_len, pg, (int *)ctx->b_nch.p,
+                                                                     (ChunkLayout *)ctx->b_layout.p, (int *)ctx->b_blk_chunks.p);
         CK((exclusive_scan<int, long long>(ctx, (const int *)ctx->b_blk_chunks.p, (long long *)ctx->b_unit_base.p, n_blocks)));
         CK(cudaMemcpyAsync(&ctx->h_pin[0], (long long *)ctx->b_unit_base.p + n_blocks, sizeof(long long), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -1036,6 +1041,7 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
                                                                  (int *)ctx->b_unit_block.p);
         ChunkPlan &ch = P.ch;
         ch.nch = (int *)ctx->b_nch.p;
+        ch.layout = (const ChunkLayout *)ctx->b_layout.p;
         ch.unit_block = (int *)ctx->b_unit_block.p;
         ch.unit_base = (long long *)ctx->b_unit_base.p;
         ch.n_units = n_units;
@@ -1715,6 +1721,8 @@ extern "C" int rt_set_option(rt_ctx *ctx, const char *name, double value) {
         ctx->opt_eval_waves = (int)value;
     else if (n == "march")
         ctx->opt_march = value != 0.0;
+    else if (n == "band_chunks")
+        ctx->opt_band_chunks = value != 0.0;
     else if (n == "pool_slots" && value >= 0.0)
         ctx->opt_pool_slots = (long long)value;
     else if (n == "pool_extra" && value >= 0.0)

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kTopoThreads, RT_TOPO_MIN_BLOCKS) k_topo(const
     const unsigned long long pol_stream = FILL ? l2_policy_stream() : 0ull;
     int pb = REC ? (int)(cidx - P.pool_slot_base) : 0;  // MODE 2: block of the pool that is being filled
     bool recording = REC;
-    constexpr double kKappa = 1.0 / 64.0;  // smallest sine of a crossing angle the cheap filter accepts
+    constexpr double kKappa = 1.0 / RT_KAPPA_INV;  // smallest sine of a crossing angle the cheap filter accepts
     bool cheap_ok = false;                 // x-ordering of entry/exit is decided by the track direction, beyond rounding
     double ang_thr = 0.0;
 

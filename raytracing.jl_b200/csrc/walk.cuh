@@ -35,6 +35,7 @@ struct TrackSoA {
 // chunk bookkeeping; per-chunk arrays are indexed cidx = unit*32 + lane, consecutive chunks of a track are 32 apart
 struct ChunkPlan {
     int *nch;               // per track: number of chunks (>= 1)
+    const struct ChunkLayout *layout;  // per track: where the chunks start (k_plan_chunks)
     int *unit_block;        // per warp-unit: which block of 32 consecutive tracks
     long long *unit_base;   // per block: first unit; [n_blocks] = n_units
     long long n_units;
@@ -84,19 +85,90 @@ struct WalkParams {
 constexpr int kRecBlock = 256;  // records per pool block (a multiple of 32): with the default chunks of ~128 segments a walker
                                 // rarely needs a second block, so the claiming atomic stays off the hot path
 
+// smallest sine of a crossing angle the cheap filter of the sign-test walks accepts is 1 / RT_KAPPA_INV ("cheap filter")
+#ifndef RT_KAPPA_INV
+#define RT_KAPPA_INV 64.0
+#endif
 enum { MODE_FAST = 0, MODE_SLOW = 1, MODE_DONE = 2 };
 constexpr int kFastBatch = 16;
 constexpr long long kRunaway = 4000000;
 constexpr int kMaxChunksPerTrack = 4096;
 
 // ---- chunk planning -----------------------------------------------------------------------------------
-__global__ void k_plan_chunks(long long n_tracks, const double *len, double chunk_len, int *nch, int *blk_chunks) {
+// Chunk layout of a track.  Every track starts and ends on the bounding box; while it is within one cell of a bounding-box line
+// it walks through boundary-band cells, where every transition is examined exactly on the slow side of the walk kernels (several
+// microseconds instead of one gather).  For the angles closest to the axes that stretch is dozens of cells long at each end (the
+// whole track for the rows next to the boundary): one regular chunk of it is a serial chain that outlasts the rest of the launch.
+// Such a head / tail is therefore cut into 8x shorter chunks:
+//     [0, head) in n_head chunks | the middle in n_mid regular chunks | [len - tail, len) in the remaining chunks
+struct ChunkLayout {
+    float head, tail;  // lengths of the finely chunked ends (0: none)
+    int n_head, n_mid;
+};
+struct PlanGeom {
+    const double *px, *py, *qx, *qy;
+    double bbmin[2], bbmax[2];
+    double band;  // width of the boundary band that counts (the longest mesh edge); 0: uniform chunks only
+};
+
+// length of the initial part of a track of length `len` whose coordinate a(s) = a0 + s * (a1 - a0) / len stays within `band` of lo / hi
+__device__ __forceinline__ double prefix_in_band(double len, double a0, double a1, double lo, double hi, double band) {
+    const double da = (a1 - a0) / len;
+    double r = 0.0;
+    if (a0 < lo + band) r = fmax(r, da > 0.0 ? fmin(len, (lo + band - a0) / da) : len);
+    if (a0 > hi - band) r = fmax(r, da < 0.0 ? fmin(len, (hi - band - a0) / da) : len);
+    return r;
+}
+
+// seed point of chunk j (0 <= j <= n) as a distance from the track's start
+__device__ __forceinline__ double chunk_start(const ChunkLayout &L, double len, int n, int j) {
+    if (L.n_head == 0 && L.n_mid == n) return len * ((double)j / (double)n);  // uniform (the common case)
+    const double head = (double)L.head, tail = (double)L.tail;
+    if (j < L.n_head) return head * ((double)j / (double)L.n_head);
+    if (j < L.n_head + L.n_mid) return head + (len - head - tail) * ((double)(j - L.n_head) / (double)L.n_mid);
+    const int n_tail = n - L.n_head - L.n_mid;
+    return n_tail > 0 ? (len - tail) + tail * ((double)(j - L.n_head - L.n_mid) / (double)n_tail) : len;
+}
+
+__global__ void k_plan_chunks(long long n_tracks, const double *len, double chunk_len, const __grid_constant__ PlanGeom G, int *nch,
+                              ChunkLayout *layout, int *blk_chunks) {
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     int n = 0;
     if (t < n_tracks) {
-        double r = ceil(len[t] / chunk_len);
-        n = (r >= 1.0) ? (r > (double)kMaxChunksPerTrack ? kMaxChunksPerTrack : (int)r) : 1;
+        const double l = len[t];
+        auto count = [](double x) { return x >= 1.0 ? (x > (double)kMaxChunksPerTrack ? kMaxChunksPerTrack : (int)x) : 1; };
+        ChunkLayout L{0.0f, 0.0f, 0, 0};
+        double head = 0.0, tail = 0.0;
+        if (isfinite(chunk_len) && G.band > 0.0 && l > 0.0) {
+            head = fmax(prefix_in_band(l, G.px[t], G.qx[t], G.bbmin[0], G.bbmax[0], G.band),
+                        prefix_in_band(l, G.py[t], G.qy[t], G.bbmin[1], G.bbmax[1], G.band));
+            tail = fmax(prefix_in_band(l, G.qx[t], G.px[t], G.bbmin[0], G.bbmax[0], G.band),
+                        prefix_in_band(l, G.qy[t], G.py[t], G.bbmin[1], G.bbmax[1], G.band));
+            if (!(head > 0.25 * chunk_len)) head = 0.0;  // an ordinary end: a few band cells, not worth chunks of its own
+            if (!(tail > 0.25 * chunk_len)) tail = 0.0;
+        }
+        if (head == 0.0 && tail == 0.0) {
+            n = count(ceil(l / chunk_len));
+            L.n_mid = n;
+        } else if (head + tail >= l) {  // the whole track runs along the boundary
+            n = count(ceil(l / (chunk_len / 8.0)));
+            L.n_mid = n;
+        } else {
+            const int nh = head > 0.0 ? count(ceil(head / (chunk_len / 8.0))) : 0, nt = tail > 0.0 ? count(ceil(tail / (chunk_len / 8.0))) : 0;
+            const int nm = count(ceil((l - head - tail) / chunk_len));
+            if (nh + nm + nt <= kMaxChunksPerTrack) {
+                n = nh + nm + nt;
+                L.head = (float)head;
+                L.tail = (float)tail;
+                L.n_head = nh;
+                L.n_mid = nm;
+            } else {
+                n = count(ceil(l / chunk_len));
+                L.n_mid = n;
+            }
+        }
         nch[t] = n;
+        layout[t] = L;
     }
     int mx = __reduce_max_sync(0xffffffffu, n);
     if ((threadIdx.x & 31) == 0 && t < n_tracks) blk_chunks[t >> 5] = mx;
@@ -133,7 +205,8 @@ __global__ void k_unit_keys(const __grid_constant__ WalkParams P, int G, int *ke
     int n = P.ch.nch[t];
     int jj = min(j, n - 1);
     int az = P.t.azim[t];
-    double s = P.t.len[t] * (((double)jj + 0.5) / (double)n);
+    const ChunkLayout L = P.ch.layout[t];
+    double s = 0.5 * (chunk_start(L, P.t.len[t], n, jj) + chunk_start(L, P.t.len[t], n, jj + 1));
     double x = P.t.px[t] + s * P.ang.cosp[az], y = P.t.py[t] + s * P.ang.sinp[az];
     double fx = (x - P.m.bbmin[0]) / (P.m.bbmax[0] - P.m.bbmin[0]), fy = (y - P.m.bbmin[1]) / (P.m.bbmax[1] - P.m.bbmin[1]);
     int ix = min(max((int)(fx * G), 0), G - 1), iy = min(max((int)(fy * G), 0), G - 1);
@@ -185,14 +258,19 @@ __global__ void __launch_bounds__(128) k_seed(const __grid_constant__ WalkParams
     if (j == 0) return;
     int az = P.t.azim[t];
     Line trk{P.t.a[t], P.t.b[t], P.t.c[t]};
-    double s = P.t.len[t] * ((double)j / (double)n);
+    double s = chunk_start(P.ch.layout[t], P.t.len[t], n, j);
     double x = P.t.px[t] + s * P.ang.cosp[az], y = P.t.py[t] + s * P.ang.sinp[az];
     bool right = P.ang.phi[az] < kPi / 2;
     int c = find_element(m, x, y, 2, nullptr);
     if (c < 0) return;
     const CellRec &r = m.cells[c];
-    double clear = (double)r.clear;
-    if (!(clear >= 0.0) || !isfinite(clear)) return;  // boundary-band or degenerate cells never seed
+    if (!isfinite(r.clear)) return;  // degenerate cells never seed
+    // Boundary-band cells (clear stored negative) seed only when the whole chord keeps the distance from the bounding box that
+    // the fast path asks of an entry point (checked below).  Exactness never depends on this test (a seed cell the serial walk
+    // does not push just costs the work of the chunks behind it, see DESIGN.md "chunks"); without such seeds a track that runs
+    // along a boundary row of cells is walked by ONE thread from end to end.
+    const bool band = r.clear < 0.0f;
+    double clear = (double)fabsf(r.clear);
     double g = sqrt(trk.a * trk.a + trk.b * trk.b);
     if (!cell_clean(r, trk, g, clear)) return;
     // the seed point itself must be well inside (not merely tolerantly inside) the cell
@@ -211,6 +289,10 @@ __global__ void __launch_bounds__(128) k_seed(const __grid_constant__ WalkParams
     if (e_q < 0 || e_p < 0) return;
     double l = norm2(p.x - q.x, p.y - q.y);
     if (!(l > P.lmin)) return;
+    if (band) {
+        const double need = 0.25 * l + 8.0 * P.tiny;
+        if (!(bbox_dist(m, p.x, p.y) > need && bbox_dist(m, q.x, q.y) > need && bbox_dist(m, x, y) > need)) return;
+    }
     P.ch.seed_cell[cidx] = c;
     P.ch.seed_kexit[cidx] = e_q;
     P.ch.seed_qx[cidx] = q.x;
