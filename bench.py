@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 RTOL = 1e-6
 
 
-def load_workload(name, n_gpus):
+def load_workload(name, n_gpus, strong=False):
     import raytracing_jl_b200 as rt
 
     if name == "pincell":
@@ -39,7 +39,7 @@ def load_workload(name, n_gpus):
         model, n_azim, delta = rt.UnstructuredDiscreteModel(d["node_coordinates"], d["cell_ptrs"], d["cell_data"]), 8, 2e-2
     else:
         model, n_azim, delta = rt.synth.workload(name)
-    return model, n_azim, delta / n_gpus
+    return model, n_azim, delta if strong else delta / n_gpus
 
 
 def peaks():
@@ -146,7 +146,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    model, n_azim, delta = load_workload(args.workload, args.gpus)
+    model, n_azim, delta = load_workload(args.workload, args.gpus, args.strong)
     threads = os.cpu_count() or 1
     budget = 2.0e7 / max(1, args.steps + args.warmup) * 3
     tot_s, tot_t, sample = 0, 0.0, ""
@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--clock-period-ms", type=float, default=20.0)
+    ap.add_argument("--strong", action="store_true", help="N > 1: shard the named workload itself (fixed total work) instead of delta / N")
     ap.add_argument("--pipeline", type=int, default=None, help="rt_set_option('pipeline'): 0 hybrid, 1 sequential, 2 two-stage, 3 single-walk")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -210,7 +211,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rt.build()
-    model, n_azim, delta = load_workload(args.workload, world)
+    model, n_azim, delta = load_workload(args.workload, world, args.strong)
     mesh = rt.Mesh(model)
     bcs = rt.BoundaryConditions(top=rt.Reflective, bottom=rt.Reflective, right=rt.Reflective, left=rt.Reflective)
     tg = rt.TrackGenerator(mesh, n_azim, delta, bcs=bcs, device=local, shard=(rank, world))
@@ -321,7 +322,7 @@ def main():
 
     if rank == 0:
         out = {"metric": "segments/sec for segmentize!", "value": value, "unit": "segments/s", "n_gpus": world, "steps": args.steps,
-               "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+               "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, model, n_azim, delta),
                "segments_per_step": nseg, "tracks": ntrk, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
                "gpu_launches": int(st["launches"] + 1) * args.steps,
