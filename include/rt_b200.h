@@ -222,8 +222,9 @@ int rt_selftest_division(rt_ctx *ctx, int64_t n_threads, uint64_t seed, int32_t 
  * "pipeline" (3: ONE sign-test walk that counts and records every chunk + one lane per segment [default]; 0: sign-test count
  * walk + geometric fill walk; 1: sequential geometric walks only; 2: sign-test count walk + sign-test record walk + one thread
  * per segment.  0, 2 and 3 verify themselves and restart in mode 1 on any disagreement; 3 restarts in mode 0 when its record
- * pool runs out), "march" (0: k_topo<2> instead of k_march in pipeline 3), "pool_slots" / "pool_extra" (test hooks: chunk slots
- * per count batch, spare record blocks), "eval_waves", "debug_verify_fail" (test hook) */
+ * pool runs out), "march" (0: k_topo<2> instead of k_march in pipeline 3), "band_chunks" (0: uniform chunks also where a track
+ * runs along the bounding box), "pool_slots" / "pool_extra" (test hooks: chunk slots per count batch, spare record blocks),
+ * "eval_waves", "debug_verify_fail" (test hook) */
 int rt_set_option(rt_ctx *ctx, const char *name, double value);
 /* CUDA-event stopwatch on the context's launching stream (bench harness: torch.cuda.Event cannot see it). */
 int rt_timer_start(rt_ctx *ctx);

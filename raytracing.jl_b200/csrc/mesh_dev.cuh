@@ -410,9 +410,10 @@ __device__ RT_SLOWPATH_INLINE void knn_query(const DevMesh &m, double x, double 
 
 // point_in_triangle  src/mesh.jl:158-176 ; lambda = R \ r by the StaticArrays 3x3 closed form
 __device__ __forceinline__ bool point_in_triangle(const DevMesh &m, int cell, double x, double y) {
-    const int *nid = &m.cell_nodes[3 * cell];
-    double2 a = m.xy[nid[0]], b = m.xy[nid[1]], c = m.xy[nid[2]];
-    double x1 = a.x, y1 = a.y, x2 = b.x, y2 = b.y, x3 = c.x, y3 = c.y;
+    // vertex coordinates from the cell record (two adjacent 32-B sectors; the same values as xy[cell_nodes[3*cell + k]], which
+    // cost two dependent gather levels)
+    const CellRec &r = m.cells[cell];
+    double x1 = r.vx[0], y1 = r.vy[0], x2 = r.vx[1], y2 = r.vy[1], x3 = r.vx[2], y3 = r.vy[2];
     double d = x1 * (y2 - y3) + y1 * (x3 - x2) + (x2 * y3 - y2 * x3);
     double l1 = ((y2 - y3) * x + (x3 - x2) * y + (x2 * y3 - x3 * y2)) / d;
     double l2 = ((y3 - y1) * x + (x1 - x3) * y + (x3 * y1 - x1 * y3)) / d;
