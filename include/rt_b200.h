@@ -211,6 +211,9 @@ int rt_info(rt_ctx *ctx, const char *key, double *value);
 /* CUDA-event time (ms) of the last call's device work, by phase: 0 upload+prep, 1 trace, 2 count,
  * 3 scan, 4 fill, 5 volumes(+allreduce) */
 int rt_phase_ms(rt_ctx *ctx, double ms[6]);
+/* diagnostics of the last rt_segmentize's chunk plan (after the fix-up): {chunks with work, void seeds, mean and max segments per
+ * working chunk, sum over the warp units of their longest / of their mean chunk (lane balance of the walk), chunk slots, warp units} */
+int rt_debug_chunk_stats(rt_ctx *ctx, double out[8]);
 
 /* self-test: 64*n_threads random quotients x/d (exponents within +-exp_span of 1.0, zeros, powers of two, all-ones
  * mantissas) through the shared-reciprocal division the walk kernels use, compared bit for bit with the IEEE `/`. */

@@ -98,6 +98,7 @@ SYMBOLS = {
     "rt_comm_init": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_char_p]),
     "rt_stats": (C.c_int, [_vp, _f64]),
     "rt_phase_ms": (C.c_int, [_vp, _f64]),
+    "rt_debug_chunk_stats": (C.c_int, [_vp, _f64]),
     "rt_info": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_double)]),
     "rt_set_option": (C.c_int, [_vp, C.c_char_p, C.c_double]),
     "rt_selftest_division": (C.c_int, [_vp, C.c_int64, C.c_uint64, C.c_int32, C.POINTER(C.c_int64)]),

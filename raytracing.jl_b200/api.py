@@ -472,6 +472,11 @@ class TrackGenerator(TrackLayout):
         self._segments = None
         return f
 
+    def chunk_stats(self):
+        s = np.zeros(8)
+        _lib.check(self._ctx, _lib.lib().rt_debug_chunk_stats(self._ctx, s))
+        return dict(zip(["working_chunks", "void_seeds", "mean_segments", "max_segments", "sum_unit_max", "sum_unit_mean", "slots", "units"], s.tolist()))
+
     def phase_ms(self):
         ms = np.zeros(6)
         _lib.lib().rt_phase_ms(self._ctx, ms)

@@ -312,6 +312,9 @@ __global__ void __launch_bounds__(kMarchThreads, RT_MARCH_MIN_BLOCKS) k_march(co
     float clearA = S.clearA;
     int f = S.f, recording = S.recording;
     const unsigned long long pol_keep = l2_policy_keep();
+#ifdef RT_MARCH_DIAG
+    unsigned diag_tot = 0, diag_done = 0, diag_wait = 0;  // lane-slots of the fast loop: all / finished lanes / lanes waiting for the slow side
+#endif
 
     while (__any_sync(FULL, mode != MODE_DONE)) {
         // ------------------------------------------------------------------ FAST phase: sign tests only
@@ -321,6 +324,11 @@ __global__ void __launch_bounds__(kMarchThreads, RT_MARCH_MIN_BLOCKS) k_march(co
             // lanes that need the slow side wait for it; leave the fast phase once kMarchWait of them do (the slow phase
             // costs a few hundred instructions per entry, an idle lane costs a lane of every fast iteration)
             if ((it & 1) && __popc(__ballot_sync(FULL, mode == MODE_SLOW || mode == MODE_RETRY)) >= kMarchWait) break;
+#ifdef RT_MARCH_DIAG
+            diag_tot++;
+            if (mode == MODE_DONE) diag_done++;
+            else if (mode != MODE_FAST) diag_wait++;
+#endif
             if (mode != MODE_FAST) continue;
             bool ok = false;
             if (enc >= 0) {
@@ -410,6 +418,11 @@ __global__ void __launch_bounds__(kMarchThreads, RT_MARCH_MIN_BLOCKS) k_march(co
     if (P.counters) {
         unsigned long long v = active ? (unsigned long long)(nseg - S.n_litpush) : 0ull;
         unsigned long long li = S.lit_iters, q0 = S.nn_q, q1 = S.knn_q;
+#ifdef RT_MARCH_DIAG
+        li = diag_done;
+        q0 = diag_wait;
+        q1 = diag_tot;
+#endif
         for (int o = 16; o > 0; o >>= 1) {
             v += __shfl_down_sync(FULL, v, o);
             li += __shfl_down_sync(FULL, li, o);

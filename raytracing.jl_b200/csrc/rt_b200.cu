@@ -1680,6 +1680,66 @@ extern "C" int rt_info(rt_ctx *ctx, const char *key, double *value) {
     return RT_OK;
 }
 
+// diagnostics of the last chunk plan (tools/): out = {chunks with work, void seeds (j >= 1), mean segments per working chunk,
+// max segments of a chunk, sum over the units of their longest chunk, sum over the units of their mean chunk, chunk slots, units}
+extern "C" int rt_debug_chunk_stats(rt_ctx *ctx, double out[8]) {
+    if (!ctx || !out || !ctx->segmented || ctx->n_units <= 0) return fail(ctx, RT_ERR_ARG, "rt_debug_chunk_stats: call rt_segmentize first");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const long long n = ctx->n_shard, n_units = ctx->n_units, n_blocks = (n + 31) / 32;
+    const size_t nc = (size_t)n_units * 32;
+    std::vector<int> nch((size_t)n), ublk((size_t)n_units), seed(nc), cnt(nc);
+    std::vector<long long> ubase((size_t)n_blocks + 1);
+    CK(cudaMemcpy(nch.data(), ctx->b_nch.p, sizeof(int) * nch.size(), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ublk.data(), ctx->b_unit_block.p, sizeof(int) * ublk.size(), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ubase.data(), ctx->b_unit_base.p, sizeof(long long) * ubase.size(), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(seed.data(), ctx->b_ch_i.p, sizeof(int) * nc, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cnt.data(), (const int *)ctx->b_ch_i.p + 2 * nc, sizeof(int) * nc, cudaMemcpyDeviceToHost));
+    double work = 0, voids = 0, sum = 0, mx = 0;
+    for (long long u = 0; u < n_units; ++u) {
+        const long long b = ublk[(size_t)u];
+        const int j = (int)(u - ubase[(size_t)b]);
+        for (int l = 0; l < 32; ++l) {
+            const long long t = 32 * b + l;
+            if (t >= n || j >= nch[(size_t)t]) continue;
+            const size_t c = (size_t)u * 32 + l;
+            if (j >= 1 && seed[c] < 0) voids += 1;
+            if (cnt[c] > 0) {
+                work += 1;
+                sum += cnt[c];
+                mx = std::max(mx, (double)cnt[c]);
+            }
+        }
+    }
+    const double mean = work > 0 ? sum / work : 0.0;
+    // how evenly a unit's work is spread over its 32 lanes: sum over the units of the LONGEST chunk (what the warp has to wait for)
+    // and of the mean chunk of the unit
+    double over15 = 0, over2 = 0;
+    for (long long u = 0; u < n_units; ++u) {
+        const long long b = ublk[(size_t)u];
+        const int j = (int)(u - ubase[(size_t)b]);
+        double umax = 0, usum = 0;
+        for (int l = 0; l < 32; ++l) {
+            const long long t = 32 * b + l;
+            if (t >= n || j >= nch[(size_t)t]) continue;
+            const double c = (double)std::max(cnt[(size_t)u * 32 + l], 0);
+            umax = std::max(umax, c);
+            usum += c;
+        }
+        over15 += umax;
+        over2 += usum / 32.0;
+    }
+    out[0] = work;
+    out[1] = voids;
+    out[2] = mean;
+    out[3] = mx;
+    out[4] = over15;
+    out[5] = over2;
+    out[6] = (double)nc;
+    out[7] = (double)n_units;
+    return RT_OK;
+}
+
 extern "C" int rt_phase_ms(rt_ctx *ctx, double ms[6]) {
     if (!ctx || !ms) return RT_ERR_ARG;
     cudaSetDevice(ctx->device);

@@ -44,6 +44,7 @@ def run(label, flags=0, reps=4, chk=False, **opts):
 small = name in ("cfg3", "cfg2", "pincell")
 c0 = run("hybrid (0)", pipeline=0, chk=small)
 c3 = run("single-walk (3)", pipeline=3, chk=small)
+print("chunk stats:", tg.chunk_stats(), flush=True)
 if small:
     print("checksums equal:", c0 == c3, flush=True)
 c3t = run("single-walk (3), k_topo<2>", pipeline=3, march=0, chk=small)
