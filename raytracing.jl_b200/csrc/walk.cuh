@@ -87,7 +87,7 @@ constexpr int kRecBlock = 256;  // records per pool block (a multiple of 32): wi
 
 // smallest sine of a crossing angle the cheap filter of the sign-test walks accepts is 1 / RT_KAPPA_INV ("cheap filter")
 #ifndef RT_KAPPA_INV
-#define RT_KAPPA_INV 64.0
+#define RT_KAPPA_INV 1024.0
 #endif
 enum { MODE_FAST = 0, MODE_SLOW = 1, MODE_DONE = 2 };
 constexpr int kFastBatch = 16;
