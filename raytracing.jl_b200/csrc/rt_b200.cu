@@ -732,7 +732,8 @@ static double lmin_of(const DevMesh &m, double tiny_step) {
 // evaluate it -- in sub-batches when its segments exceed the resident capacity.  *next_mode = 0 asks the caller to repeat the
 // call with the hybrid pipeline (pool exhausted: the mesh is far denser along some chunks than the Cauchy-Crofton estimate).
 static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_vol, rt_batch_cb cb, void *cb_user, int attempt,
-                             bool *verify_failed, int *next_mode, double *launches_io, double est_total) {
+                             bool *verify_failed, int *next_mode, double *launches_io, double est_total, bool *deferred_verify) {
+    *deferred_verify = false;
     cudaStream_t st = ctx->stream;
     const long long n = ctx->n_shard;
     const long long n_blocks = (n + 31) / 32;
@@ -934,6 +935,15 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
             toc(ctx, 4);
             ctx->h_pin[2] = 0;
             CK(cudaMemcpyAsync(&ctx->h_pin[2], ctx->b_verify.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            if (!cb && !multi && !split) {
+                // one batch, nobody waits for it: the verification flag is read with the final read-back of the call
+                // (segmentize_once), which saves one host synchronisation per call; the fill time is collected lazily
+                *deferred_verify = true;
+                ctx->phase_ms[2] = acc[2];
+                ctx->phase_ms[3] = acc[3];
+                *launches_io += launches;
+                return RT_OK;
+            }
             CK(cudaStreamSynchronize(st));
             take(4);
             if ((int)ctx->h_pin[2]) {
@@ -972,6 +982,7 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
     const long long n = ctx->n_shard;
     const bool single = mode == 3 && n > 0;
     double est_total_segments = 0.0;
+    bool deferred_verify = false;
     const int n2 = ctx->n2;
     DevMesh &m = ctx->m;
     const bool want_vol = !(flags & RT_SEG_NO_VOLUMES);
@@ -1101,7 +1112,8 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         ctx->eval_ms = 0.0;
         P.counters = (unsigned long long *)ctx->b_counters.p;
         int next_mode = 1;
-        int rc = segmentize_single(ctx, P, rtol, want_vol, cb, cb_user, attempt, verify_failed, &next_mode, &launches, est_total_segments);
+        int rc = segmentize_single(ctx, P, rtol, want_vol, cb, cb_user, attempt, verify_failed, &next_mode, &launches, est_total_segments,
+                                   &deferred_verify);
         if (rc) return rc;
         if (*verify_failed) {
             ctx->fallback_mode = next_mode;
@@ -1280,6 +1292,10 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
     }
     CK(cudaMemcpyAsync(&ctx->h_pin[4], ctx->b_counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (deferred_verify && (int)ctx->h_pin[2]) {
+        *verify_failed = true;
+        return RT_OK;
+    }
     if (n > 0) bad = (unsigned long long)ctx->h_pin[3];
     unsigned long long hc[4];
     for (int q = 0; q < 4; ++q) hc[q] = (unsigned long long)ctx->h_pin[4 + q];
