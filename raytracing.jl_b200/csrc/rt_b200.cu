@@ -124,6 +124,16 @@ struct rt_ctx {
     NcclApi nccl;
     ncclComm_t comm = nullptr;
     int n_ranks = 1, rank = 0;
+    // The all-reduce of the volumes runs on its own stream, so that the next segmentize! of the caller overlaps with it: the
+    // per-element sums are accumulated alternately in b_vol / b_vol_alt, the collective reads the one just filled.
+    cudaStream_t coll_stream = nullptr;
+    DevBuf b_vol_alt;
+    int vol_cur = 0;
+    double *vol_acc = nullptr;                              // accumulation buffer of the current / last rt_segmentize
+    cudaEvent_t ev_fill_done = nullptr;                     // ctx->stream: the sums are complete
+    cudaEvent_t ev_vol_free[2] = {nullptr, nullptr};        // coll_stream: the collective has consumed buffer i (and b_voln is ready)
+    bool ev_vol_used[2] = {false, false};
+    int voln_ready = -1;                                    // index of the event that marks b_voln complete (-1: main stream)
 };
 
 static int fail(rt_ctx *c, int code, const char *fmt, ...) {
@@ -221,11 +231,17 @@ extern "C" void rt_destroy(rt_ctx *ctx) {
                      &ctx->b_scratch, &ctx->b_gcounts,   &ctx->b_gcursor,
                      &ctx->b_omega,   &ctx->b_sigma,     &ctx->b_tau,
                      &ctx->b_pool,    &ctx->b_pool_next, &ctx->b_pool_cursor,
-                     &ctx->b_area,    &ctx->b_factor,    &ctx->b_layout};
+                     &ctx->b_area,    &ctx->b_factor,    &ctx->b_layout,    &ctx->b_vol_alt};
     for (DevBuf *b : all) release(*b);
     for (int ph = 0; ph < 6; ++ph)
         for (int q = 0; q < 2; ++q)
             if (ctx->pev[ph][q]) cudaEventDestroy(ctx->pev[ph][q]);
+    if (ctx->coll_stream) {
+        cudaStreamSynchronize(ctx->coll_stream);
+        cudaStreamDestroy(ctx->coll_stream);
+    }
+    for (cudaEvent_t e : {ctx->ev_fill_done, ctx->ev_vol_free[0], ctx->ev_vol_free[1]})
+        if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     delete ctx;
@@ -881,7 +897,7 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
         P.oqy = ctx->s_qy;
         P.olen = ctx->s_len;
         P.oelem = ctx->s_elem;
-        P.vol = want_vol ? (double *)ctx->b_vol.p : nullptr;
+        P.vol = want_vol ? ctx->vol_acc : nullptr;
         EvalParams E{};
         E.m = P.m;
         E.t = ctx->t;
@@ -988,7 +1004,7 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
     const bool want_vol = !(flags & RT_SEG_NO_VOLUMES);
     *verify_failed = false;
     *bad_out = ~0ULL;
-    if (want_vol) CK(cudaMemsetAsync(ctx->b_vol.p, 0, sizeof(double) * (size_t)m.n_cells, st));
+    if (want_vol) CK(cudaMemsetAsync(ctx->vol_acc, 0, sizeof(double) * (size_t)m.n_cells, st));
     size_t nn = (size_t)std::max<long long>(n, 1);
     CK(cudaMemsetAsync(ctx->b_counters.p, 0, sizeof(unsigned long long) * 4, st));
     CK(cudaMemsetAsync(ctx->b_bad.p, 0xff, sizeof(unsigned long long), st));
@@ -1097,7 +1113,7 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         if (topo_count) {
             k_topo<0><<<blocks_for(n_units * 32, kTopoThreads), kTopoThreads, 0, st>>>(P);
         } else {
-            P.vol = (want_vol && count_only) ? (double *)ctx->b_vol.p : nullptr;
+            P.vol = (want_vol && count_only) ? ctx->vol_acc : nullptr;
             k_walk<false><<<blocks_for(n_units * 32, kWalkThreads), kWalkThreads, 0, st>>>(P);
         }
         k_fixup_tracks<<<blocks_for(n, 128), 128, 0, st>>>(P);
@@ -1168,7 +1184,7 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         P.oelem = ctx->s_elem;
         P.rec = (int *)ctx->b_rec.p;
         P.tsum = topo_count ? (double *)ctx->b_tsum.p : nullptr;
-        P.vol = want_vol ? (double *)ctx->b_vol.p : nullptr;
+        P.vol = want_vol ? ctx->vol_acc : nullptr;
         P.counters = nullptr;
         EvalParams E{};
         E.m = m;
@@ -1335,6 +1351,15 @@ extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rt
         CK(cudaMemcpyAsync((double *)ctx->b_ang_d.p + 6 * (size_t)n2, delta_eff, sizeof(double) * n2, cudaMemcpyHostToDevice, st));
         ctx->has_delta = true;
         CK(ensure(ctx->b_vol, sizeof(double) * (size_t)m.n_cells));
+        ctx->vol_acc = (double *)ctx->b_vol.p;
+        if (ctx->comm && ctx->coll_stream) {  // alternate, and wait until the collective of two calls ago has released the buffer
+            ctx->vol_cur ^= 1;
+            if (ctx->vol_cur) {
+                CK(ensure(ctx->b_vol_alt, sizeof(double) * (size_t)m.n_cells));
+                ctx->vol_acc = (double *)ctx->b_vol_alt.p;
+            }
+            if (ctx->ev_vol_used[ctx->vol_cur]) CK(cudaStreamWaitEvent(st, ctx->ev_vol_free[ctx->vol_cur], 0));
+        }
     }
     size_t nn = (size_t)std::max<long long>(n, 1);
     CK(ensure(ctx->b_count, sizeof(int) * nn));
@@ -1531,6 +1556,7 @@ extern "C" int rt_correct_volumes(rt_ctx *ctx, double *factors, const double **d
     if (rc) return rc;
     cudaStream_t st = ctx->stream;
     const int nc = ctx->m.n_cells;
+    if (ctx->voln_ready >= 0) CK(cudaStreamWaitEvent(st, ctx->ev_vol_free[ctx->voln_ready], 0));  // the all-reduced volumes
     CK(ensure(ctx->b_factor, sizeof(double) * (size_t)nc));
     k_volume_factors<<<blocks_for(nc, 256), 256, 0, st>>>(nc, (const double *)ctx->b_area.p, (const double *)ctx->b_voln.p, (double *)ctx->b_factor.p);
     if (ctx->res_nseg > 0)
@@ -1583,6 +1609,13 @@ extern "C" int rt_comm_init(rt_ctx *ctx, int32_t n_ranks, int32_t rank, const ch
     memcpy(u.internal, id, 128);
     ncclResult_t r = ctx->nccl.CommInitRank(&ctx->comm, n_ranks, u, rank);
     if (r != 0) return fail(ctx, RT_ERR_NCCL, "ncclCommInitRank: %s", ctx->nccl.GetErrorString ? ctx->nccl.GetErrorString(r) : "?");
+    if (!ctx->coll_stream) {
+        if (cudaStreamCreateWithFlags(&ctx->coll_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_fill_done, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_vol_free[0], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_vol_free[1], cudaEventDisableTiming) != cudaSuccess)
+            return fail(ctx, RT_ERR_CUDA, "rt_comm_init: cannot create the collective stream");
+    }
     ctx->n_ranks = n_ranks;
     ctx->rank = rank;
     return RT_OK;
@@ -1594,17 +1627,32 @@ extern "C" int rt_volumes(rt_ctx *ctx, double *volumes) {
     cudaStream_t st = ctx->stream;
     int nc = ctx->m.n_cells;
     CK(ensure(ctx->b_voln, sizeof(double) * (size_t)nc));
-    tic(ctx, 5);
-    const double *src = (const double *)ctx->b_vol.p;
-    if (ctx->comm) {
-        // the ONLY collective of the path: sum of per-element delta*len over the uid shards
-        ncclResult_t r = ctx->nccl.AllReduce(ctx->b_vol.p, ctx->b_voln.p, (size_t)nc, ncclFloat64, ncclSum, ctx->comm, st);
+    const double *src = ctx->vol_acc ? ctx->vol_acc : (const double *)ctx->b_vol.p;
+    if (ctx->comm && ctx->coll_stream) {
+        // the ONLY collective of the path: sum of per-element delta*len over the uid shards -- on its own stream, behind the
+        // evaluation that produced the sums and in front of nothing but the next collective
+        cudaStream_t cs = ctx->coll_stream;
+        CK(cudaEventRecord(ctx->ev_fill_done, st));
+        CK(cudaStreamWaitEvent(cs, ctx->ev_fill_done, 0));
+        CK(cudaEventRecord(ctx->pev[5][0], cs));
+        ncclResult_t r = ctx->nccl.AllReduce(src, ctx->b_voln.p, (size_t)nc, ncclFloat64, ncclSum, ctx->comm, cs);
         if (r != 0) return fail(ctx, RT_ERR_NCCL, "ncclAllReduce: %s", ctx->nccl.GetErrorString ? ctx->nccl.GetErrorString(r) : "?");
-        src = (const double *)ctx->b_voln.p;
+        k_normalise<<<blocks_for(nc, 256), 256, 0, cs>>>((const double *)ctx->b_voln.p, (double *)ctx->b_voln.p, nc, (double)ctx->n2);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->pev[5][1], cs));
+        ctx->pev_dirty[5] = true;
+        CK(cudaEventRecord(ctx->ev_vol_free[ctx->vol_cur], cs));
+        ctx->ev_vol_used[ctx->vol_cur] = true;
+        ctx->voln_ready = ctx->vol_cur;
+        if (volumes) CK(cudaStreamSynchronize(cs));
+    } else {
+        tic(ctx, 5);
+        k_normalise<<<blocks_for(nc, 256), 256, 0, st>>>(src, (double *)ctx->b_voln.p, nc, (double)ctx->n2);
+        CK(cudaGetLastError());
+        toc(ctx, 5);
+        ctx->voln_ready = -1;
+        if (volumes) CK(cudaStreamSynchronize(st));  // (the copy below runs on the legacy stream, which does not wait for ours)
     }
-    k_normalise<<<blocks_for(nc, 256), 256, 0, st>>>(src, (double *)ctx->b_voln.p, nc, (double)ctx->n2);
-    CK(cudaGetLastError());
-    toc(ctx, 5);
     if (volumes) CK(cudaMemcpy(volumes, ctx->b_voln.p, sizeof(double) * (size_t)nc, cudaMemcpyDeviceToHost));
     return RT_OK;
 }
@@ -1767,6 +1815,7 @@ extern "C" int rt_phase_ms(rt_ctx *ctx, double ms[6]) {
 extern "C" int rt_timer_start(rt_ctx *ctx) {
     if (!ctx) return RT_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
+    if (ctx->coll_stream) CK(cudaStreamSynchronize(ctx->coll_stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventRecord(ctx->tev[0], ctx->stream));
     return RT_OK;
@@ -1774,6 +1823,7 @@ extern "C" int rt_timer_start(rt_ctx *ctx) {
 
 extern "C" int rt_timer_stop(rt_ctx *ctx, double *elapsed_ms) {
     if (!ctx || !elapsed_ms) return RT_ERR_ARG;
+    if (ctx->voln_ready >= 0) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_vol_free[ctx->voln_ready], 0));  // outstanding collective
     CK(cudaEventRecord(ctx->tev[1], ctx->stream));
     CK(cudaEventSynchronize(ctx->tev[1]));
     float ms = 0.f;
