@@ -191,8 +191,11 @@ int rt_correct_volumes(rt_ctx *ctx, double *factors, const double **d_factors);
 
 /* ---- volumes: replaces the tail of fill_volumes (src/trackgenerator.jl:378-386) -----------------------
  * volumes[e] = (sum over this context's segments of delta_eff[azim]*len) / n_azim_2, after an NCCL
- * all-reduce across the communicator set up with rt_comm_init (skipped when there is none). */
-int rt_volumes(rt_ctx *ctx, double *volumes /* n_cells */);
+ * all-reduce across the communicator set up with rt_comm_init (skipped when there is none).  With a communicator the
+ * collective runs on a stream of its own, ordered behind the rt_segmentize that produced the sums: with volumes == NULL the
+ * call only enqueues it (it then overlaps with the caller's next rt_segmentize); with a host pointer the call waits for it and
+ * copies the result.  Every rank must call rt_volumes once per rt_segmentize, in the same order. */
+int rt_volumes(rt_ctx *ctx, double *volumes /* n_cells, or NULL */);
 
 /* ---- multi-GPU: one context per process/GPU, tracks sharded by uid range, mesh replicated -----------
  * rank 0 calls rt_comm_unique_id and ships the 128 bytes to the other ranks (MPI / torch.distributed /
