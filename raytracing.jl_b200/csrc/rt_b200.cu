@@ -219,6 +219,8 @@ extern "C" int rt_create(rt_ctx **out, int device) {
 extern "C" void rt_destroy(rt_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->coll_stream) cudaStreamSynchronize(ctx->coll_stream);  // a collective may still be in flight
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
     DevBuf *all[] = {&ctx->b_xy,      &ctx->b_cell_nodes, &ctx->b_nc_ptrs,  &ctx->b_nc_data, &ctx->b_nbr,     &ctx->b_cells,
                      &ctx->b_edges,   &ctx->b_qual,       &ctx->b_bdist,    &ctx->b_sc,      &ctx->b_grid_ptrs, &ctx->b_grid_nodes,
