@@ -117,3 +117,25 @@ def test_mesh_tables_are_gridap_layout(pincell_model, pincell_mesh):
         for c in cells:
             assert node in pincell_model.cell_data[3 * (c - 1):3 * c]
     assert pincell_mesh.bb_min.tolist() == [0.0, 0.0] and pincell_mesh.bb_max.tolist() == [1.6, 1.6]
+
+
+def test_reference_arm_contract():
+    """bench.py --impl reference (the CPU arm the driver runs next to ours): ONE JSON line on rank 0 with the contract's keys,
+    nothing from the other ranks."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--workload", "pincell"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, "RANK": "0", "WORLD_SIZE": "1"})
+    assert out.returncode == 0, out.stderr
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "segments/sec for segmentize!" and d["unit"] == "segments/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    out = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, timeout=300, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"})
+    assert out.returncode == 0 and out.stdout.strip() == ""
