@@ -912,6 +912,10 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
         E.rtol = rtol;
         const bool split = batch_total > cap;
         if (split) {
+            if (h_unit_base.empty()) {  // (one walk batch whose segments do not fit after all: the unit ranges are needed now)
+                h_unit_base.resize((size_t)n_blocks + 1);
+                CK(cudaMemcpyAsync(h_unit_base.data(), ctx->b_unit_base.p, sizeof(long long) * h_unit_base.size(), cudaMemcpyDeviceToHost, st));
+            }
             h_off.resize((size_t)(e - b) + 1);
             CK(cudaMemcpyAsync(h_off.data(), (long long *)ctx->b_offsets.p + b, sizeof(long long) * h_off.size(), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
