@@ -186,7 +186,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--clock-period-ms", type=float, default=20.0)
     ap.add_argument("--strong", action="store_true", help="N > 1: shard the named workload itself (fixed total work) instead of delta / N")
-    ap.add_argument("--pipeline", type=int, default=None, help="rt_set_option('pipeline'): 0 hybrid, 1 sequential, 2 two-stage, 3 single-walk")
+    ap.add_argument("--pipeline", type=int, default=None, help="rt_set_option('pipeline'): 0 hybrid, 1 sequential, 3 single-walk")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -272,8 +272,8 @@ def main():
     alg_bytes = 44.0 * nseg_local + 72.0 * (tg.uid_end - tg.uid_begin) + 40.0 * model.num_cells
     peak, peak_src = peaks()
     achieved = alg_bytes / (fill_ms * 1e-3) / 1e9
-    kern = {3: "k_eval3 (one lane per segment: records -> Segment columns)", 0: "k_walk<true> (fill pass)", 1: "k_walk<true> (fill pass)",
-            2: "k_topo<1> + k_eval2 (fill pass)"}[3 if args.pipeline is None else args.pipeline]
+    kern = {3: "k_eval3 (one lane per segment: records -> Segment columns)", 0: "k_walk<true> (fill pass)",
+            1: "k_walk<true> (fill pass)"}[3 if args.pipeline is None else args.pipeline]
     roofline = {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "launch_ms": fill_ms, "count_pass_ms": count_ms,

@@ -33,7 +33,8 @@ typedef enum rt_status {
     RT_ERR_NOT_TRACED = -7,    /* error("Segmentation is intended after tracing...") trackgenerator.jl:360 */
     RT_ERR_TRACK = -8,         /* a track failed; see first_bad_uid / bad_status of rt_segmentize */
     RT_ERR_NCCL = -9,
-    RT_ERR_NOMEM = -10
+    RT_ERR_NOMEM = -10,
+    RT_ERR_PEER = -11          /* rt_volumes: another rank's rt_segmentize failed (the all-reduced sums are incomplete) */
 } rt_status;
 
 /* per-track status written by rt_segmentize (the reference throws at the first such track) */
@@ -50,6 +51,8 @@ enum { RT_VACUUM = 0, RT_REFLECTIVE = 1, RT_PERIODIC = 2 };
 /* @enum DirectionType (src/track.jl:11-14) */
 enum { RT_FORWARD = 0, RT_BACKWARD = 1 };
 
+#define RT_MAX_K 32
+
 /* walk flags for rt_segmentize */
 enum {
     RT_SEG_DEFAULT = 0,
@@ -57,7 +60,7 @@ enum {
     RT_SEG_NO_VOLUMES = 2,  /* skip the fused fill_volumes accumulation */
     RT_SEG_COUNT_ONLY = 4,  /* count + scan only (no segment buffers are written) */
     RT_SEG_NO_CHUNKS = 8,   /* one walker per track (no sub-track chunks) */
-    RT_SEG_SEQUENTIAL = 16  /* sequential walk kernels only (the two-stage pipeline falls back to them by itself) */
+    RT_SEG_SEQUENTIAL = 16  /* sequential walk kernels only (the self-verifying pipelines fall back to them by themselves) */
 };
 
 /* ---- context ------------------------------------------------------------------------------------- */
@@ -115,6 +118,8 @@ int rt_plan_shards(rt_ctx *ctx, int32_t n_azim_2, const int64_t *n_tracks_x, con
  * _segmentize_track! (src/track.jl:106-178) and fill_volumes (src/trackgenerator.jl:371-386) -----------
  * count pass -> exclusive scan -> fill pass (+ fused per-element sum of delta_eff*len).
  * tiny_step: TrackGenerator kwarg; k, rtol: segmentize! kwargs; max_iter: MAX_ITER (src/track.jl:104).
+ * 1 <= k <= RT_MAX_K: the k-nearest-node fallback of find_element (src/mesh.jl:123) keeps a fixed-size candidate list;
+ * larger values are rejected with RT_ERR_ARG instead of being clamped silently (the reference has no limit).
  * delta_eff: tg.azimuthal_quadrature.deltas (n_azim_2 values) or NULL with RT_SEG_NO_VOLUMES.
  * If the shard's segments exceed the context's segment capacity (rt_set_segment_capacity) the fill runs
  * in uid batches over a recycled buffer and `cb` (may be NULL) is called once per batch.
@@ -194,7 +199,10 @@ int rt_correct_volumes(rt_ctx *ctx, double *factors, const double **d_factors);
  * all-reduce across the communicator set up with rt_comm_init (skipped when there is none).  With a communicator the
  * collective runs on a stream of its own, ordered behind the rt_segmentize that produced the sums: with volumes == NULL the
  * call only enqueues it (it then overlaps with the caller's next rt_segmentize); with a host pointer the call waits for it and
- * copies the result.  Every rank must call rt_volumes once per rt_segmentize, in the same order. */
+ * copies the result.  Every rank must call rt_volumes once per rt_segmentize, in the same order -- ALSO when its rt_segmentize
+ * returned an error (RT_ERR_TRACK leaves valid sums; after any other error the rank joins the collective with a zero contribution
+ * and raises a flag that travels with the sums): the call then returns that rank's error, and every rank that asks for the
+ * volumes (host pointer) gets RT_ERR_PEER instead of silently incomplete sums.  Nobody is left waiting inside the all-reduce. */
 int rt_volumes(rt_ctx *ctx, double *volumes /* n_cells, or NULL */);
 
 /* ---- multi-GPU: one context per process/GPU, tracks sharded by uid range, mesh replicated -----------
@@ -207,7 +215,7 @@ int rt_comm_init(rt_ctx *ctx, int32_t n_ranks, int32_t rank, const char id[128])
  * stats[0..7] of the last rt_segmentize: kernel launches, fast transitions, slow (literal) iterations,
  * nearest-node queries, knn queries, count-pass ms, fill-pass ms, scan+volumes ms. */
 int rt_stats(rt_ctx *ctx, double stats[8]);
-/* named scalars: "verify_fallbacks", "eval_ms" (stage 2 of the two-stage fill), "n_units", "segment_capacity", "count_batches"
+/* named scalars: "verify_fallbacks", "n_units", "segment_capacity", "count_batches"
  * (uid batches of the single-walk pipeline's count walk) of the last rt_segmentize; "tau_ms" (k_tau alone) of the last
  * rt_optical_lengths */
 int rt_info(rt_ctx *ctx, const char *key, double *value);
@@ -226,11 +234,11 @@ int rt_selftest_division(rt_ctx *ctx, int64_t n_threads, uint64_t seed, int32_t 
  * "target_walkers" (chunks are sized so that about this many walkers exist, default 148*2048*4),
  * "order_grid" (G: walkers are launched in Morton order of a G x G tiling of the domain, default 32, 0 = uid order),
  * "pipeline" (3: ONE sign-test walk that counts and records every chunk + one lane per segment [default]; 0: sign-test count
- * walk + geometric fill walk; 1: sequential geometric walks only; 2: sign-test count walk + sign-test record walk + one thread
- * per segment.  0, 2 and 3 verify themselves and restart in mode 1 on any disagreement; 3 restarts in mode 0 when its record
+ * walk + geometric fill walk; 1: sequential geometric walks only.  0 and 3 verify themselves and restart in mode 1 on any
+ * disagreement; 3 restarts in mode 0 when its record
  * pool runs out), "march" (0: k_topo<2> instead of k_march in pipeline 3), "band_chunks" (0: uniform chunks also where a track
  * runs along the bounding box), "pool_slots" / "pool_extra" (test hooks: chunk slots per count batch, spare record blocks),
- * "eval_waves", "debug_verify_fail" (test hook) */
+ * "debug_verify_fail" (test hook) */
 int rt_set_option(rt_ctx *ctx, const char *name, double value);
 /* CUDA-event stopwatch on the context's launching stream (bench harness: torch.cuda.Event cannot see it). */
 int rt_timer_start(rt_ctx *ctx);

@@ -123,7 +123,7 @@ class OracleMesh:
         return lib().orc_nn_brute(self._h, x, y)
 
     def knn(self, x, y, k, skip):
-        ids = np.zeros(8, np.int32)
+        ids = np.zeros(32, np.int32)  # ORC_MAX_K
         n = lib().orc_knn(self._h, x, y, k, skip, ids)
         return ids[:n].copy()
 
@@ -198,6 +198,8 @@ class OracleTrackGenerator:
         rc = lib().orc_segmentize(self._h, k, rtol, uid_begin, uid_end, nthreads, C.byref(nseg), C.byref(bad))
         if rc == -7:
             raise OracleError(self._ERR[rc])
+        if rc == -8:
+            raise OracleError(f"k = {k} outside [1, 32] (ORC_MAX_K of the restatement; the reference has no limit)")
         self.n_segments = nseg.value
         self.first_bad_uid, self.bad_status = bad.value, rc
         nt = uid_end - uid_begin

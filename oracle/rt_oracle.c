@@ -170,8 +170,8 @@ static int32_t kd_build(orc_mesh *m, int32_t lo, int32_t hi) {
 
 typedef struct {
     int k, n;
-    double d2[8];
-    int32_t id[8];
+    double d2[ORC_MAX_K];
+    int32_t id[ORC_MAX_K];
     int32_t skip; /* 0-based id to skip or -1 */
 } knn_state;
 
@@ -221,7 +221,7 @@ int32_t orc_nn(const orc_mesh *m, double x, double y) {
 
 int orc_knn(const orc_mesh *m, double x, double y, int k, int32_t skip, int32_t *ids) {
     knn_state s;
-    if (k > 8) k = 8;
+    if (k > ORC_MAX_K) k = ORC_MAX_K; /* orc_segmentize rejects k > ORC_MAX_K, so this never truncates a walk */
     s.k = k;
     s.n = 0;
     s.skip = skip - 1;
@@ -339,7 +339,7 @@ static int32_t find_element_ex(const orc_mesh *m, double x, double y, int k, int
     int32_t c = scan_node_cells(m, nn_id, x, y);
     if (c > 0) return c;
     if (used_knn) *used_knn = 1;
-    int32_t ids[8];
+    int32_t ids[ORC_MAX_K];
     int n = orc_knn(m, x, y, k, nn_id, ids);
     for (int i = 0; i < n; ++i) {
         c = scan_node_cells(m, ids[i], x, y);
@@ -867,6 +867,7 @@ static int walk_track(const orc_tg *t, int64_t u, orc_segvec *v, int k, double r
 int orc_segmentize(orc_tg *t, int k, double rtol, int64_t uid_begin, int64_t uid_end, int nthreads,
                    int64_t *n_segments, int64_t *first_bad_uid) {
     if (!t->traced) return ORC_E_NOT_TRACED; /* src/trackgenerator.jl:360-361 */
+    if (k < 1 || k > ORC_MAX_K) return ORC_E_BAD_K;
     if (!t->segs) t->segs = (orc_segvec *)calloc((size_t)t->n_total, sizeof(orc_segvec));
     if (uid_begin < 1) uid_begin = 1;
     if (uid_end > t->n_total + 1) uid_end = t->n_total + 1;
@@ -880,7 +881,7 @@ int orc_segmentize(orc_tg *t, int k, double rtol, int64_t uid_begin, int64_t uid
         {
             int64_t st[8] = {0};
             int64_t loc = 0;
-#pragma omp for schedule(dynamic, 16)
+#pragma omp for schedule(dynamic, 1)
             for (int64_t uid = uid_begin; uid < uid_end; ++uid) {
                 orc_segvec *v = &t->segs[uid - 1];
                 v->status = walk_track(t, uid - 1, v, k, rtol, st);

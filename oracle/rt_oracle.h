@@ -31,8 +31,10 @@ enum { ORC_OK = 0, ORC_ERR_TRY_K = 1, ORC_ERR_LENGTH = 2, ORC_ERR_RUNAWAY = 3, O
 /* error codes of orc_tg_create / orc_trace */
 enum {
     ORC_E_NAZIM_POS = -1, ORC_E_NAZIM_MULT4 = -2, ORC_E_DELTA_POS = -3, ORC_E_NO_EXIT = -4,
-    ORC_E_BC_MISMATCH = -5, ORC_E_NOT_ON_BOUNDARY = -6, ORC_E_NOT_TRACED = -7
+    ORC_E_BC_MISMATCH = -5, ORC_E_NOT_ON_BOUNDARY = -6, ORC_E_NOT_TRACED = -7, ORC_E_BAD_K = -8
 };
+/* largest `k` of segmentize!(t; k) the restatement's fixed-size candidate list holds (the reference has no limit) */
+#define ORC_MAX_K 32
 
 /* Mesh (src/mesh.jl:24-31).  CSR tables are 1-based exactly as Gridap stores them. Arrays are copied. */
 orc_mesh *orc_mesh_create(int32_t n_nodes, const double *xy, int32_t n_cells, const int32_t *cell_ptrs,

@@ -6,6 +6,7 @@ point raises.  ``build()`` compiles the library in-tree with nvcc for sm_100a.
 from __future__ import annotations
 
 import ctypes as C
+import glob
 import os
 import subprocess
 
@@ -15,7 +16,6 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SO_PATH = os.environ.get("RT_B200_LIB") or os.path.join(_PKG, "librt_b200.so")  # RT_B200_LIB: an alternative build
 _CSRC = os.path.join(_PKG, "csrc")
-_SOURCES = ["rt_b200.cu", "geom.cuh", "mesh_dev.cuh", "walk.cuh", "topo.cuh", "eval.cuh", "sweep.cuh", "trace.cuh", "scan.cuh"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -30,11 +30,13 @@ class RTError(RuntimeError):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """nvcc -gencode arch=compute_100a,code=sm_100a ... -> raytracing.jl_b200/librt_b200.so"""
-    srcs = [os.path.join(_CSRC, s) for s in _SOURCES] + [os.path.join(_ROOT, "include", "rt_b200.h")]
-    if (not force) and os.path.exists(SO_PATH) and all(os.path.getmtime(SO_PATH) >= os.path.getmtime(s) for s in srcs):
+    # every file under csrc/ is a dependency (rt_b200.cu includes all the .cuh files), plus the public header
+    main = os.path.join(_CSRC, "rt_b200.cu")
+    deps = sorted(glob.glob(os.path.join(_CSRC, "*.cu")) + glob.glob(os.path.join(_CSRC, "*.cuh"))) + [os.path.join(_ROOT, "include", "rt_b200.h")]
+    if (not force) and os.path.exists(SO_PATH) and all(os.path.getmtime(SO_PATH) >= os.path.getmtime(s) for s in deps):
         return SO_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH, srcs[0], "-ldl"]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH, main, "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
@@ -137,27 +139,40 @@ def ptr(a):
     return None if a is None else a.ctypes.data_as(_vp)
 
 
-class PinnedArray:
-    """numpy view over cudaHostAlloc'ed memory (rt_host_alloc)."""
+class _PinnedBlock:
+    """Owns one cudaHostAlloc allocation; freed when the last numpy view of it is gone (or explicitly)."""
 
-    def __init__(self, shape, dtype):
-        self.dtype = np.dtype(dtype)
-        n = int(np.prod(shape))
-        self._p = _vp()
-        rc = lib().rt_host_alloc(C.byref(self._p), max(1, n * self.dtype.itemsize))
+    def __init__(self, nbytes):
+        self.p = _vp()
+        rc = lib().rt_host_alloc(C.byref(self.p), max(1, nbytes))
         if rc:
             raise RTError(rc, "rt_host_alloc failed")
-        buf = (C.c_char * (n * self.dtype.itemsize)).from_address(self._p.value)
-        self.array = np.frombuffer(buf, dtype=self.dtype, count=n).reshape(shape)
 
     def free(self):
-        if self._p:
-            self.array = None
-            lib().rt_host_free(self._p)
-            self._p = None
+        if self.p:
+            lib().rt_host_free(self.p)
+            self.p = None
 
     def __del__(self):
         try:
             self.free()
         except Exception:
             pass
+
+
+class PinnedArray:
+    """numpy view over cudaHostAlloc'ed memory (rt_host_alloc).  The allocation is owned by the buffer object every view of
+    ``array`` keeps alive through its ``base`` chain: dropping the PinnedArray never frees memory a view still points into.
+    ``free()`` releases it at once -- only for buffers whose views the caller controls (the staged mesh arrays)."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        n = int(np.prod(shape))
+        self._block = _PinnedBlock(n * self.dtype.itemsize)
+        buf = (C.c_char * (n * self.dtype.itemsize)).from_address(self._block.p.value)
+        buf._owner = self._block  # numpy view -> memoryview -> buf -> block
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=n).reshape(shape)
+
+    def free(self):
+        self.array = None
+        self._block.free()

@@ -160,9 +160,16 @@ class Track:  # src/track.jl:42-57 ; a view over the track SoA
 
     @property
     def segments(self):
-        off = self._tg.segment_offsets
-        base = self._tg._resident_base
-        return SegmentList(self._tg, int(off[self._i] - base), int(off[self._i + 1] - base))
+        tg = self._tg
+        off = tg.segment_offsets
+        u0, u1, base, n = tg.resident_batch()
+        if not u0 <= self.uid < u1:  # batched fill (rt_set_segment_capacity / a shard larger than memory): only one batch is resident
+            raise LookupError(f"segments of track uid {self.uid} are not resident: the device holds the batch of uids [{u0}, {u1}) "
+                              "(consume earlier batches through segmentize_(..., on_batch=...))")
+        lo, hi = int(off[self._i] - base), int(off[self._i + 1] - base)
+        if not 0 <= lo <= hi <= n:
+            raise IndexError(f"segment range [{lo}, {hi}) of track uid {self.uid} outside the resident batch of {n} segments")
+        return SegmentList(tg, lo, hi)
 
     def __repr__(self):
         return f"Track(uid={self.uid}, azim_idx={self.azim_idx}, track_idx={self.track_idx}, p={self.p}, q={self.q})"
@@ -299,7 +306,7 @@ class TrackGenerator(TrackLayout):
         self._track_data = None
         self._segments = None
         self._offsets = None
-        self._resident_base = 0
+        self._resident = None
         self.n_segments = 0
 
     def _mesh_arrays(self):
@@ -334,7 +341,7 @@ class TrackGenerator(TrackLayout):
             _lib.check(self._ctx, L.rt_mesh_bbox(self._ctx, lo, hi))
             mesh.bb_min, mesh.bb_max = lo, hi
         self._traced = self._segmented = False
-        self._track_data = self._segments = self._offsets = None
+        self._track_data = self._segments = self._offsets = self._resident = None
 
     def device_node_cells(self):
         """The vertex->cells table as the device holds it (1-based CSR like Gridap's Table)."""
@@ -391,15 +398,26 @@ class TrackGenerator(TrackLayout):
             self.fetch_segments()
         return self._segments
 
-    def fetch_segments(self, pinned: bool = True):
-        """Device -> host copy of the Segment records (into reusable pinned buffers by default)."""
+    def resident_batch(self):
+        """(uid_begin, uid_end, offset_base, n_segments) of the Segment batch the device holds (``rt_segments_device``), read
+        when first needed after a segmentize_ and dropped whenever the segments are invalidated."""
+        if self._resident is None:
+            if not self._segmented:
+                raise RuntimeError("call segmentize_ first")
+            view = _lib.rt_batch()
+            _lib.check(self._ctx, _lib.lib().rt_segments_device(self._ctx, C.byref(view)))
+            self._resident = (int(view.uid_begin), int(view.uid_end), int(view.offset_base), int(view.n_segments))
+        return self._resident
+
+    def fetch_segments(self, pinned: bool = False):
+        """Device -> host copy of the Segment records of the resident batch.  By default into fresh numpy arrays the caller owns.
+        ``pinned=True`` stages into page-locked buffers that are REUSED by the next pinned fetch of this TrackGenerator (full PCIe
+        rate, no allocation per call): the arrays returned by an earlier pinned fetch then show the new data.  A buffer that has
+        to grow is never freed under a view that is still alive (its memory is released when the last view dies)."""
         if not self._segmented:
             raise RuntimeError("call segmentize_ first")
         L = _lib.lib()
-        view = _lib.rt_batch()
-        _lib.check(self._ctx, L.rt_segments_device(self._ctx, C.byref(view)))
-        n = int(view.n_segments)
-        self._resident_base = int(view.offset_base)
+        n = self.resident_batch()[3]
         names = [("px", np.float64), ("py", np.float64), ("qx", np.float64), ("qy", np.float64), ("len", np.float64),
                  ("element", np.int32)]
         out = {}
@@ -407,9 +425,7 @@ class TrackGenerator(TrackLayout):
             if pinned:
                 buf = self._pinned.get(name)
                 if buf is None or buf.array.shape[0] < n:
-                    if buf is not None:
-                        buf.free()
-                    buf = _lib.PinnedArray((max(n, 1),), dt)
+                    buf = _lib.PinnedArray((max(n, 1),), dt)  # (the old buffer lives on for as long as views of it do)
                     self._pinned[name] = buf
                 out[name] = buf.array[:n]
             else:
@@ -500,9 +516,9 @@ class TrackGenerator(TrackLayout):
 
     def close(self):
         if getattr(self, "_ctx", None):
-            for b in list(self._pinned.values()) + list(getattr(self, "_pinned_mesh", None) or []):
+            for b in list(getattr(self, "_pinned_mesh", None) or []):
                 b.free()
-            self._pinned = {}
+            self._pinned = {}  # (result buffers are released when the last numpy view of them dies)
             self._pinned_mesh = None
             self._segments = None
             _lib.lib().rt_destroy(self._ctx)
@@ -562,7 +578,7 @@ def trace_(tg: TrackGenerator) -> TrackGenerator:
         tg.uid_begin, tg.uid_end = 1, tg.n_total_tracks + 1
     tg._traced = False
     tg._segmented = False
-    tg._track_data = tg._segments = tg._offsets = None
+    tg._track_data = tg._segments = tg._offsets = tg._resident = None
     rc = L.rt_trace(tg._ctx, n2, tg.n_tracks_x, tg.n_tracks_y, aq.phis, sin_t, cos_t, tan_t, dxe, dye, tg.bcs.codes(),
                     tg.uid_begin, tg.uid_end)
     if rc == -4:
@@ -611,7 +627,7 @@ def segmentize_(tg: TrackGenerator, k: int = 5, rtol: float = RTOL_DEFAULT, flag
     if not tg._traced:
         raise RuntimeError("Segmentation is intended after tracing. Please, call `trace!` first!")
     tg._segmented = False
-    tg._segments = tg._offsets = None
+    tg._segments = tg._offsets = tg._resident = None
     nseg, bad_uid, bad_status = C.c_int64(0), C.c_int64(0), C.c_int32(0)
     delta = tg.azimuthal_quadrature.deltas
     rc = L.rt_segmentize(tg._ctx, tg.tiny_step, int(k), float(rtol), int(max_iter), _lib.ptr(delta), int(flags),
@@ -622,16 +638,27 @@ def segmentize_(tg: TrackGenerator, k: int = 5, rtol: float = RTOL_DEFAULT, flag
         raise err
     tg.n_segments = int(nseg.value)
     tg.first_bad_uid, tg.bad_status = int(bad_uid.value), int(bad_status.value)
-    if rc == -8:
-        tg._segmented = True
-        if check:
-            _lib.check(tg._ctx, rc)
-    else:
-        _lib.check(tg._ctx, rc)
-        tg._segmented = True
-    if not (flags & _lib.RT_SEG_NO_VOLUMES):
-        _lib.check(tg._ctx, L.rt_volumes(tg._ctx, _lib.ptr(tg.volumes) if fetch_volumes else None))
+    want_vol = not (flags & _lib.RT_SEG_NO_VOLUMES)
+    if rc not in (0, -8):
+        # every rank of a communicator has to enter the all-reduce once per segmentize! -- a rank that failed joins it with a
+        # zero contribution and the failed-rank flag (rt_volumes), so that its peers are not left waiting; then the error is raised
+        msg = L.rt_last_error(tg._ctx)
+        if want_vol and getattr(tg, "_has_comm", False):
+            L.rt_volumes(tg._ctx, None)
+        raise _lib.RTError(rc, msg.decode() if msg else "")
+    tg._segmented = True
+    err = None
+    if rc == -8 and check:  # a track failed like it does in the reference (src/track.jl:141,172); the other tracks are segmentized
+        msg = L.rt_last_error(tg._ctx)
+        err = _lib.RTError(rc, msg.decode() if msg else "")
+    if want_vol:
+        rcv = L.rt_volumes(tg._ctx, _lib.ptr(tg.volumes) if fetch_volumes else None)
+        if err is not None:
+            raise err  # (after the collective: the peers of this rank are not left inside ncclAllReduce)
+        _lib.check(tg._ctx, rcv)
         # volume_correction = true: the reference's TODO (src/trackgenerator.jl:388), applied when every segment is resident
         if tg.volume_correction and on_batch is None and not (flags & _lib.RT_SEG_COUNT_ONLY) and tg.info("segment_capacity") >= tg.n_segments:
             tg.volume_factors = tg.correct_volumes()
+    elif err is not None:
+        raise err
     return tg

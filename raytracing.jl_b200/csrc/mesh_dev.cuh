@@ -340,7 +340,9 @@ __global__ void k_grid_fill(DevMesh m, const int *ptrs, int *cursor, int *nodes)
 // literal point location
 // ------------------------------------------------------------------------------------------------
 
-constexpr int kMaxK = 8;
+// largest `k` of segmentize!(t; k) (src/mesh.jl:123): the candidate list of the exact kNN search is a fixed-size array;
+// rt_segmentize rejects larger values with RT_ERR_ARG (the reference itself has no limit)
+constexpr int kMaxK = 32;
 
 struct KBest {
     double d2[kMaxK];
@@ -439,7 +441,7 @@ __device__ RT_SLOWPATH_INLINE int find_element(const DevMesh &m, double x, doubl
     int nn = s.id[0];
     int c = scan_node_cells(m, nn, x, y);
     if (c >= 0) return c;
-    s.k = min(k, kMaxK);
+    s.k = min(k, kMaxK);  // (k <= kMaxK is checked by rt_segmentize)
     knn_query(m, x, y, nn, s);
     if (nq) nq[1]++;
     for (int i = 0; i < s.n; ++i) {

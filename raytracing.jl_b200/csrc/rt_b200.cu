@@ -15,7 +15,6 @@
 
 #include "scan.cuh"
 #include "sweep.cuh"
-#include "eval.cuh"
 #include "eval3.cuh"
 #include "march.cuh"
 #include "topo.cuh"
@@ -80,29 +79,27 @@ struct rt_ctx {
     DevBuf b_layout;  // per-track chunk layout (walk.cuh ChunkLayout)
     DevBuf b_nch, b_blk_chunks, b_unit_base, b_unit_block, b_ch_i, b_ch_d;  // chunk plan (walk.cuh ChunkPlan)
     DevBuf b_order, b_okeys, b_ohist;  // spatial execution order of the units
-    DevBuf b_evalblk, b_trkrec;
     DevBuf b_omega, b_sigma, b_tau;  // sweep-facing exports (sweep.cuh)
     DevBuf b_area, b_factor;         // exact element volumes, volume-correction factors (sweep.cuh)
     bool area_valid = false;
     long long *h_pin = nullptr;  // page-locked scratch for the small device->host read-backs of rt_segmentize (16 words)
     DevBuf b_scratch, b_gcounts, b_gcursor;  // rt_mesh_upload staging (kept between uploads)
-    DevBuf b_rec, b_verify, b_tsum;    // two-stage pipeline: per-segment records, verification flag, per-track length sums
+    DevBuf b_verify, b_tsum;    // self-verifying pipelines: verification flag, per-track length sums
     DevBuf b_pool, b_pool_next, b_pool_cursor;  // single-walk pipeline: record blocks (walk.cuh kRecBlock), chain, cursor
     int count_batches = 0;             // single-walk pipeline: how many uid batches the count walk needed (info)
     int opt_band_chunks = 1;           // 8x shorter chunks for tracks that run along the bounding box (walk.cuh k_plan_chunks)
     int opt_march = 1;                 // single-walk pipeline: k_march (register-resident loop) instead of k_topo<2>
     long long opt_pool_slots = 0;      // test hook: at most this many chunk slots per count batch (0: as many as fit)
     double opt_pool_extra = 1.25;      // spare pool blocks, as a multiple of (expected segments / kRecBlock)
-    int opt_pipeline = 3;              // 3: single walk (k_march counts AND records, k_eval3 evaluates) [default]; 0: hybrid (sign-test count walk + geometric fill walk), 1: sequential (walk.cuh only),
-                                       // 2: two-stage (sign-test walks + one thread per segment); 0 and 2 fall back to 1
+    int opt_pipeline = 3;              // 3: single walk (k_march counts AND records, k_eval3 evaluates) [default]; 0: hybrid (sign-test count walk +
+                                       // geometric fill walk), 1: sequential (walk.cuh only); 3 falls back to 0 (pool exhausted) or 1, 0 falls back to 1
     int verify_fallbacks = 0;
     int fallback_mode = 1;             // pipeline to repeat the call with after a failed verification
     int opt_debug_verify_fail = 0;     // test hook: make the verification of the two-stage pipeline fail
-    double eval_ms = 0.0, tau_ms = 0.0;
+    double tau_ms = 0.0;
     cudaEvent_t ev2[2] = {nullptr, nullptr};
     int opt_order_grid = 32;           // G x G tiles (0: identity order)
     int n_sm = 148;
-    int opt_eval_waves = 1;            // k_eval2 grid = n_sm * resident blocks * this
     long long n_units = 0;
     double opt_chunk_segments = 128.0;              // minimum expected segments per chunk
     double opt_target_walkers = 148.0 * 2048.0 * 4.0;  // chunks are sized so that about this many walkers exist
@@ -229,7 +226,7 @@ extern "C" void rt_destroy(rt_ctx *ctx) {
                      &ctx->b_voln,    &ctx->b_counters,   &ctx->b_bad,      &ctx->b_seg_d,   &ctx->b_seg_e,
                      &ctx->b_twin,    &ctx->b_he,         &ctx->b_node_reach,
                      &ctx->b_nch,     &ctx->b_blk_chunks, &ctx->b_unit_base, &ctx->b_unit_block, &ctx->b_ch_i, &ctx->b_ch_d,
-                     &ctx->b_order,   &ctx->b_okeys,      &ctx->b_ohist,     &ctx->b_rec,     &ctx->b_verify,    &ctx->b_tsum,      &ctx->b_evalblk,   &ctx->b_trkrec,
+                     &ctx->b_order,   &ctx->b_okeys,      &ctx->b_ohist,     &ctx->b_verify,    &ctx->b_tsum,
                      &ctx->b_scratch, &ctx->b_gcounts,   &ctx->b_gcursor,
                      &ctx->b_omega,   &ctx->b_sigma,     &ctx->b_tau,
                      &ctx->b_pool,    &ctx->b_pool_next, &ctx->b_pool_cursor,
@@ -993,13 +990,13 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
 //   mode 1 (sequential): k_walk<false> counts, k_walk<true> fills (walk.cuh);
 //   mode 0 (hybrid):     k_topo<0> counts by sign tests (topo.cuh), k_walk<true> fills and re-derives the same decisions
 //                        from the exact geometry;
-//   mode 2 (two-stage):  k_topo<0> counts, k_topo<1> writes per-segment records, k_eval evaluates one segment per thread.
-// In modes 0 and 2 the length check (src/track.jl:171-175) runs after the fill (k_track_status).  *verify_failed reports that
-// the fill disagreed with the count (mode 0) or that a segment broke a geometric fast-path condition (mode 2): the caller then
+//   mode 3 (single walk): segmentize_single above.
+// In modes 0 and 3 the length check (src/track.jl:171-175) runs after the fill (k_track_status).  *verify_failed reports that
+// the fill disagreed with the count (mode 0) or that a segment broke a geometric fast-path condition (mode 3): the caller then
 // repeats the call in mode 1.
 static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol, int32_t max_iter, uint32_t flags, rt_batch_cb cb,
                            void *cb_user, int mode, int attempt, bool *verify_failed, unsigned long long *bad_out) {
-    const bool topo = mode == 2, topo_count = mode != 1;
+    const bool topo_count = mode != 1;
     cudaStream_t st = ctx->stream;
     const long long n = ctx->n_shard;
     const bool single = mode == 3 && n > 0;
@@ -1010,7 +1007,7 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
     const bool want_vol = !(flags & RT_SEG_NO_VOLUMES);
     *verify_failed = false;
     *bad_out = ~0ULL;
-    if (want_vol) CK(cudaMemsetAsync(ctx->vol_acc, 0, sizeof(double) * (size_t)m.n_cells, st));
+    if (want_vol) CK(cudaMemsetAsync(ctx->vol_acc, 0, sizeof(double) * ((size_t)m.n_cells + 1), st));  // (+1: the failed-rank flag of rt_volumes)
     size_t nn = (size_t)std::max<long long>(n, 1);
     CK(cudaMemsetAsync(ctx->b_counters.p, 0, sizeof(unsigned long long) * 4, st));
     CK(cudaMemsetAsync(ctx->b_bad.p, 0xff, sizeof(unsigned long long), st));
@@ -1131,7 +1128,6 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         ctx->res_trk_begin = ctx->res_trk_end = 0;
         ctx->res_off_base = 0;
         ctx->res_nseg = 0;
-        ctx->eval_ms = 0.0;
         P.counters = (unsigned long long *)ctx->b_counters.p;
         int next_mode = 1;
         int rc = segmentize_single(ctx, P, rtol, want_vol, cb, cb_user, attempt, verify_failed, &next_mode, &launches, est_total_segments,
@@ -1162,7 +1158,6 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
     if (!single) {
         ctx->phase_ms[4] = 0.0;
         ctx->pev_dirty[4] = false;
-        ctx->eval_ms = 0.0;
         ctx->res_trk_begin = ctx->res_trk_end = 0;
         ctx->res_off_base = 0;
         ctx->res_nseg = 0;
@@ -1171,13 +1166,11 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         long long cap = total;
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
-        const double bytes_per_seg = topo ? 48.0 : 44.0;
-        long long fit = (long long)((double)(free_b + ctx->b_seg_d.bytes + ctx->b_seg_e.bytes + ctx->b_rec.bytes) * 0.92 / bytes_per_seg);
+        long long fit = (long long)((double)(free_b + ctx->b_seg_d.bytes + ctx->b_seg_e.bytes) * 0.92 / 44.0);
         if (ctx->cap_cfg > 0) cap = std::min(cap, (long long)ctx->cap_cfg);
         cap = std::min(cap, fit);
         int rc = ensure_segment_buffers(ctx, cap);
         if (rc) return rc;
-        if (topo) CK(ensure(ctx->b_rec, sizeof(int) * (size_t)ctx->cap));
         if (topo_count) {
             CK(ensure(ctx->b_tsum, sizeof(double) * nn));
             CK(cudaMemsetAsync(ctx->b_tsum.p, 0, sizeof(double) * nn, st));
@@ -1188,7 +1181,6 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         P.oqy = ctx->s_qy;
         P.olen = ctx->s_len;
         P.oelem = ctx->s_elem;
-        P.rec = (int *)ctx->b_rec.p;
         P.tsum = topo_count ? (double *)ctx->b_tsum.p : nullptr;
         P.vol = want_vol ? ctx->vol_acc : nullptr;
         P.counters = nullptr;
@@ -1198,7 +1190,6 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         E.ang = P.ang;
         E.offsets = P.offsets;
         E.n_tracks = n;
-        E.rec = P.rec;
         E.opx = P.opx;
         E.opy = P.opy;
         E.oqx = P.oqx;
@@ -1207,16 +1198,11 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         E.oelem = P.oelem;
         E.vol = P.vol;
         E.lmin = ctx->opt_debug_verify_fail ? INFINITY : P.lmin;
-        if (ctx->opt_debug_verify_fail && !topo && topo_count) CK(cudaMemsetAsync(ctx->b_verify.p, 1, 1, st));
+        if (ctx->opt_debug_verify_fail && topo_count) CK(cudaMemsetAsync(ctx->b_verify.p, 1, 1, st));
         E.verify_fail = P.verify_fail;
         E.status = P.status;
         E.tsum = P.tsum;
         E.rtol = rtol;
-        if (topo) {
-            CK(ensure(ctx->b_trkrec, sizeof(TrackRec) * nn));
-            k_track_recs<<<blocks_for(n, 256), 256, 0, st>>>(E, n, (TrackRec *)ctx->b_trkrec.p);
-            launches += 1;
-        }
         std::vector<long long> h_off;
         if (total > cap) {
             h_off.resize((size_t)n + 1);
@@ -1243,26 +1229,7 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
                 P.unit_end = h_unit_base[(size_t)((e - 1) >> 5) + 1];
             }
             const long long nseg_b = (total > cap ? h_off[e] : total) - P.offset_base;
-            if (topo) {
-                k_topo<1><<<blocks_for((P.unit_end - P.unit_begin) * 32, kTopoThreads), kTopoThreads, 0, st>>>(P);
-                E.trk_begin = b;
-                E.trk_end = e;
-                E.offset_base = P.offset_base;
-                E.n_seg = nseg_b;
-                CK(cudaEventRecord(ctx->ev2[0], st));
-                if (nseg_b > 0) {
-                    const long long n_groups = (nseg_b + kEvalGroup - 1) / kEvalGroup;
-                    CK(ensure(ctx->b_evalblk, sizeof(int) * (size_t)n_groups));
-                    k_eval_groups<<<blocks_for(n_groups, 256), 256, 0, st>>>(E, n_groups, (int *)ctx->b_evalblk.p);
-                    const long long eb_max = (long long)ctx->n_sm * RT_EVAL_MIN_BLOCKS * ctx->opt_eval_waves;
-                    const unsigned eblocks = (unsigned)std::min<long long>(blocks_for(n_groups, kEval2Threads / 32), eb_max);
-                    k_eval2<<<eblocks, kEval2Threads, 0, st>>>(
-                        E, (const TrackRec *)ctx->b_trkrec.p, (const int *)ctx->b_evalblk.p, n_groups);
-                }
-                CK(cudaEventRecord(ctx->ev2[1], st));
-                k_track_status<<<blocks_for(e - b, 128), 128, 0, st>>>(E);
-                launches += 4;
-            } else {
+            {
                 k_walk<true><<<blocks_for((P.unit_end - P.unit_begin) * 32, kWalkThreads), kWalkThreads, 0, st>>>(P);
                 launches += 1;
                 if (topo_count) {
@@ -1284,11 +1251,6 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
                 CK(cudaMemcpyAsync(&ctx->h_pin[2], ctx->b_verify.p, sizeof(int), cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
                 const int vf = (int)ctx->h_pin[2];
-                if (topo) {
-                    float ems = 0.f;
-                    cudaEventElapsedTime(&ems, ctx->ev2[0], ctx->ev2[1]);
-                    ctx->eval_ms += ems;
-                }
                 if (vf) {
                     *verify_failed = true;
                     toc(ctx, 4);
@@ -1334,6 +1296,8 @@ extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rt
     if (!ctx->traced)
         return fail(ctx, RT_ERR_NOT_TRACED, "Segmentation is intended after tracing. Please, call `trace!` first!");
     if (k < 1 || max_iter < 0) return fail(ctx, RT_ERR_ARG, "rt_segmentize: bad k / max_iter");
+    if (k > kMaxK)
+        return fail(ctx, RT_ERR_ARG, "rt_segmentize: k = %d exceeds RT_MAX_K = %d (the k-nearest-node fallback of find_element keeps a fixed-size candidate list)", (int)k, kMaxK);
     const bool want_vol = !(flags & RT_SEG_NO_VOLUMES);
     if (want_vol && !delta_eff) return fail(ctx, RT_ERR_ARG, "rt_segmentize: delta_eff is required unless RT_SEG_NO_VOLUMES");
     CK(cudaSetDevice(ctx->device));
@@ -1356,12 +1320,12 @@ extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rt
         // (pageable source: the call returns once the n2 values are staged, no synchronisation needed before the caller reuses them)
         CK(cudaMemcpyAsync((double *)ctx->b_ang_d.p + 6 * (size_t)n2, delta_eff, sizeof(double) * n2, cudaMemcpyHostToDevice, st));
         ctx->has_delta = true;
-        CK(ensure(ctx->b_vol, sizeof(double) * (size_t)m.n_cells));
+        CK(ensure(ctx->b_vol, sizeof(double) * ((size_t)m.n_cells + 1)));
         ctx->vol_acc = (double *)ctx->b_vol.p;
         if (ctx->comm && ctx->coll_stream) {  // alternate, and wait until the collective of two calls ago has released the buffer
             ctx->vol_cur ^= 1;
             if (ctx->vol_cur) {
-                CK(ensure(ctx->b_vol_alt, sizeof(double) * (size_t)m.n_cells));
+                CK(ensure(ctx->b_vol_alt, sizeof(double) * ((size_t)m.n_cells + 1)));
                 ctx->vol_acc = (double *)ctx->b_vol_alt.p;
             }
             if (ctx->ev_vol_used[ctx->vol_cur]) CK(cudaStreamWaitEvent(st, ctx->ev_vol_free[ctx->vol_cur], 0));
@@ -1375,7 +1339,7 @@ extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rt
     CK(ensure(ctx->b_bad, sizeof(unsigned long long)));
     CK(ensure(ctx->b_verify, sizeof(int)));
 
-    // the two-stage pipeline unless a flag asks for behaviour only the sequential kernels have
+    // the configured pipeline unless a flag asks for behaviour only the sequential kernels have
     int mode = (flags & (RT_SEG_SEQUENTIAL | RT_SEG_COUNT_ONLY)) ? 1 : ctx->opt_pipeline;
     ctx->stats[0] = 0;
     ctx->verify_fallbacks = 0;
@@ -1628,29 +1592,47 @@ extern "C" int rt_comm_init(rt_ctx *ctx, int32_t n_ranks, int32_t rank, const ch
 }
 
 extern "C" int rt_volumes(rt_ctx *ctx, double *volumes) {
-    if (!ctx || !ctx->segmented || !ctx->vol_valid) return fail(ctx, RT_ERR_ARG, "rt_volumes: run rt_segmentize with volumes enabled first");
+    if (!ctx) return RT_ERR_ARG;
+    const bool have = ctx->segmented && ctx->vol_valid;
+    const bool coll = ctx->comm && ctx->coll_stream;
+    if (!have && !(coll && ctx->has_mesh)) return fail(ctx, RT_ERR_ARG, "rt_volumes: run rt_segmentize with volumes enabled first");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     int nc = ctx->m.n_cells;
-    CK(ensure(ctx->b_voln, sizeof(double) * (size_t)nc));
+    CK(ensure(ctx->b_voln, sizeof(double) * ((size_t)nc + 1)));
     const double *src = ctx->vol_acc ? ctx->vol_acc : (const double *)ctx->b_vol.p;
-    if (ctx->comm && ctx->coll_stream) {
+    if (!have) {
+        // This rank's rt_segmentize failed, but its peers are (or will be) inside the all-reduce: join it with a zero contribution
+        // and a raised flag in the extra slot, so that nobody hangs and every rank learns that the sums are incomplete.
+        CK(cudaStreamSynchronize(ctx->coll_stream));  // (an earlier collective may still be reading b_vol)
+        CK(ensure(ctx->b_vol, sizeof(double) * ((size_t)nc + 1)));
+        CK(cudaMemsetAsync(ctx->b_vol.p, 0, sizeof(double) * ((size_t)nc + 1), st));
+        const double one = 1.0;
+        CK(cudaMemcpyAsync((double *)ctx->b_vol.p + nc, &one, sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        src = (const double *)ctx->b_vol.p;
+    }
+    if (coll) {
         // the ONLY collective of the path: sum of per-element delta*len over the uid shards -- on its own stream, behind the
-        // evaluation that produced the sums and in front of nothing but the next collective
+        // evaluation that produced the sums and in front of nothing but the next collective.  Element nc of the buffers counts the
+        // ranks whose rt_segmentize failed.
         cudaStream_t cs = ctx->coll_stream;
         CK(cudaEventRecord(ctx->ev_fill_done, st));
         CK(cudaStreamWaitEvent(cs, ctx->ev_fill_done, 0));
         CK(cudaEventRecord(ctx->pev[5][0], cs));
-        ncclResult_t r = ctx->nccl.AllReduce(src, ctx->b_voln.p, (size_t)nc, ncclFloat64, ncclSum, ctx->comm, cs);
+        ncclResult_t r = ctx->nccl.AllReduce(src, ctx->b_voln.p, (size_t)nc + 1, ncclFloat64, ncclSum, ctx->comm, cs);
         if (r != 0) return fail(ctx, RT_ERR_NCCL, "ncclAllReduce: %s", ctx->nccl.GetErrorString ? ctx->nccl.GetErrorString(r) : "?");
         k_normalise<<<blocks_for(nc, 256), 256, 0, cs>>>((const double *)ctx->b_voln.p, (double *)ctx->b_voln.p, nc, (double)ctx->n2);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->pev[5][1], cs));
         ctx->pev_dirty[5] = true;
-        CK(cudaEventRecord(ctx->ev_vol_free[ctx->vol_cur], cs));
-        ctx->ev_vol_used[ctx->vol_cur] = true;
-        ctx->voln_ready = ctx->vol_cur;
-        if (volumes) CK(cudaStreamSynchronize(cs));
+        if (have) {
+            CK(cudaEventRecord(ctx->ev_vol_free[ctx->vol_cur], cs));
+            ctx->ev_vol_used[ctx->vol_cur] = true;
+            ctx->voln_ready = ctx->vol_cur;
+        }
+        if (volumes || !have) CK(cudaStreamSynchronize(cs));
+        if (!have) return fail(ctx, RT_ERR_ARG, "rt_volumes: this rank's rt_segmentize failed; it joined the all-reduce with a zero contribution and the failed-rank flag");
     } else {
         tic(ctx, 5);
         k_normalise<<<blocks_for(nc, 256), 256, 0, st>>>(src, (double *)ctx->b_voln.p, nc, (double)ctx->n2);
@@ -1659,7 +1641,15 @@ extern "C" int rt_volumes(rt_ctx *ctx, double *volumes) {
         ctx->voln_ready = -1;
         if (volumes) CK(cudaStreamSynchronize(st));  // (the copy below runs on the legacy stream, which does not wait for ours)
     }
-    if (volumes) CK(cudaMemcpy(volumes, ctx->b_voln.p, sizeof(double) * (size_t)nc, cudaMemcpyDeviceToHost));
+    if (volumes) {
+        CK(cudaMemcpy(volumes, ctx->b_voln.p, sizeof(double) * (size_t)nc, cudaMemcpyDeviceToHost));
+        if (coll) {
+            double failed = 0.0;
+            CK(cudaMemcpy(&failed, (const double *)ctx->b_voln.p + nc, sizeof(double), cudaMemcpyDeviceToHost));
+            if (failed != 0.0)
+                return fail(ctx, RT_ERR_PEER, "rt_volumes: rt_segmentize failed on %d rank(s) of the communicator: the volumes miss their tracks", (int)failed);
+        }
+    }
     return RT_OK;
 }
 
@@ -1735,8 +1725,6 @@ extern "C" int rt_info(rt_ctx *ctx, const char *key, double *value) {
     std::string k(key);
     if (k == "verify_fallbacks")
         *value = ctx->verify_fallbacks;
-    else if (k == "eval_ms")
-        *value = ctx->eval_ms;
     else if (k == "tau_ms")
         *value = ctx->tau_ms;
     else if (k == "n_units")
@@ -1847,10 +1835,8 @@ extern "C" int rt_set_option(rt_ctx *ctx, const char *name, double value) {
         ctx->opt_target_walkers = value;
     else if (n == "order_grid" && value >= 0.0 && value <= 256.0)
         ctx->opt_order_grid = (int)value;
-    else if (n == "pipeline" && (value == 0.0 || value == 1.0 || value == 2.0 || value == 3.0))
+    else if (n == "pipeline" && (value == 0.0 || value == 1.0 || value == 3.0))
         ctx->opt_pipeline = (int)value;
-    else if (n == "eval_waves" && value >= 1.0 && value <= 64.0)
-        ctx->opt_eval_waves = (int)value;
     else if (n == "march")
         ctx->opt_march = value != 0.0;
     else if (n == "band_chunks")

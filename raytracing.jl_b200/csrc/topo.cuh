@@ -1,22 +1,16 @@
-// topo.cuh -- the two-stage form of the segmentation passes.
+// topo.cuh -- sign-test walks of the half-edge graph.
 //
 // A Segment(p, q, l, element) depends only on (track, cell): intersections() uses the track's infinite line
 // (src/intersection.jl:60).  So the serial part of _segmentize_track! (src/track.jl:106-178) is only the ORDER in which
 // cells are accepted; the geometry of every accepted cell can be evaluated independently afterwards.
 //
-//   k_topo<0>  count pass: walks the half-edge graph deciding each transition from the SIGNS of the signed distances of
-//                  the cell's vertices from the track line (two multiply-adds per step, no division, no square root),
-//                  under the same clearance test as the sequential fast path (walk.cuh); everything that test does not
-//                  cover runs the literal walk of the reference, exactly as in walk.cuh.
-//   k_topo<1>   fill pass, stage 1: the same walk writes one 4-byte record per segment at its final position:
+//   k_topo<0>  count pass of the hybrid pipeline: walks the half-edge graph deciding each transition from the SIGNS of the
+//                  signed distances of the cell's vertices from the track line (two multiply-adds per step, no division, no
+//                  square root), under the same clearance test as the sequential fast path (walk.cuh); everything that test
+//                  does not cover runs the literal walk of the reference, exactly as in walk.cuh.
+//   k_topo<2>  count AND record in one walk (the reference form of k_march, march.cuh): one 4-byte record per segment
 //                  fast:  (h << 2) | (exit1 << 1)   h = entry half-edge 3*cell + k, exit1: leaves through edge k+1 (else k+2)
 //                  literal: (cell << 2) | 1
-//   k_eval2        (eval.cuh) fill pass, stage 2: ONE THREAD PER SEGMENT, coalesced.  Fast records: p and q are the reference's
-//                  intersection() of the track with the entry and exit edge lines (precomputed general_form, bit-identical
-//                  to the sequential path); literal records: the reference's intersections() on the cell.  It also checks
-//                  the three conditions of the sequential fast path that need the geometry (exit edge not parallel,
-//                  order_intersection_points puts the entry first, chord longer than l_min).  If any segment fails one, the
-//                  whole call is redone with the sequential kernels of walk.cuh (never observed on the meshes of tests/).
 //   k_track_status per track: the reference's length check (src/track.jl:171-175) on the accumulated segment lengths.
 #pragma once
 #include "walk.cuh"
@@ -67,16 +61,16 @@ __device__ __forceinline__ P2 exit_point(const DevMesh &m, const Line &trk, int 
     return X;
 }
 
-// MODE 0: count only; MODE 1: write the records at their final positions (needs the counts and offsets of an earlier MODE 0
-// pass); MODE 2: count AND record in one walk -- the records go to a pool of kRecBlock-record blocks (the chunk's first block
+// MODE 0: count only; MODE 2: count AND record in one walk -- the records go to a pool of kRecBlock-record blocks (the chunk's first block
 // is implicit, further blocks are claimed with one atomic each and chained through pool_next), from where k_eval3 (eval3.cuh)
 // evaluates them once the scan has fixed the final positions.
 template <int MODE>
 __global__ void __launch_bounds__(kTopoThreads, RT_TOPO_MIN_BLOCKS) k_topo(const __grid_constant__ WalkParams P) {
-    constexpr bool FILL = MODE == 1, REC = MODE == 2;
+    static_assert(MODE == 0 || MODE == 2, "k_topo: count (0) or count+record (2)");
+    constexpr bool REC = MODE == 2;
     const unsigned FULL = 0xffffffffu;
     const DevMesh &m = P.m;
-    __shared__ int s_rec[MODE != 0 ? 8 * kTopoThreads : 1];  // 8 records per thread = one 32-byte sector
+    __shared__ int s_rec[REC ? 8 * kTopoThreads : 1];  // 8 records per thread = one 32-byte sector
     const int tid = threadIdx.x;
     long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
@@ -93,7 +87,6 @@ __global__ void __launch_bounds__(kTopoThreads, RT_TOPO_MIN_BLOCKS) k_topo(const
     int az = 0;
     bool right = true;
     int nseg = 0, status = 0, endcode = END_TRACK;
-    long long out = 0;
     // last pushed cell and the local edge it was left through (-1: unknown); (qx, qy) is its exit point when q_valid
     int cur = -1, cur_kout = -1, enc = -1;
     bool f = false, clean = false, q_valid = false;
@@ -103,7 +96,6 @@ __global__ void __launch_bounds__(kTopoThreads, RT_TOPO_MIN_BLOCKS) k_topo(const
     const bool literal_only = (P.flags & 1u) != 0;
     bool active = false;
     const unsigned long long pol_keep = l2_policy_keep();
-    const unsigned long long pol_stream = FILL ? l2_policy_stream() : 0ull;
     int pb = REC ? (int)(cidx - P.pool_slot_base) : 0;  // MODE 2: block of the pool that is being filled
     bool recording = REC;
     constexpr double kKappa = 1.0 / RT_KAPPA_INV;  // smallest sine of a crossing angle the cheap filter accepts
@@ -128,10 +120,6 @@ __global__ void __launch_bounds__(kTopoThreads, RT_TOPO_MIN_BLOCKS) k_topo(const
         int n = P.ch.nch[t];
         int seed = (j < n) ? (j == 0 ? -2 : P.ch.seed_cell[cidx]) : -1;
         active = (seed != -1);
-        if (FILL && active) {
-            limit = P.ch.count[cidx];
-            active = limit > 0;
-        }
         if (active) {
             az = P.t.azim[t];
             ta = P.t.a[t];
@@ -142,7 +130,6 @@ __global__ void __launch_bounds__(kTopoThreads, RT_TOPO_MIN_BLOCKS) k_topo(const
             ang_thr = kKappa * g * P.lmax;
             // |X.x - q.x| = l*|cos phi| >= l_min*|b|/g must exceed the rounding error of both points, ~ 8*eps*S/kappa each
             cheap_ok = P.lmin * (fabs(tb) / g) > 32.0 * 2.220446049250313e-16 * P.smax / kKappa;
-            if (FILL) out = P.offsets[t] - P.offset_base + P.ch.prefix[cidx];
             if (j == 0) {
                 qx = P.t.px[t];  // the literal walk starts from advance_step(track.p), src/track.jl:114
                 qy = P.t.py[t];
@@ -155,22 +142,20 @@ __global__ void __launch_bounds__(kTopoThreads, RT_TOPO_MIN_BLOCKS) k_topo(const
                 q_valid = true;
                 mode = (literal_only || !clean) ? MODE_SLOW : MODE_FAST;
             }
-            if (!FILL) {
-                for (int jj = j + 1; jj < n; ++jj) {
-                    int sc = P.ch.seed_cell[cidx + 32LL * (jj - j)];
-                    if (sc >= 0) {
-                        stop_cell = sc;
-                        break;
-                    }
+            for (int jj = j + 1; jj < n; ++jj) {
+                int sc = P.ch.seed_cell[cidx + 32LL * (jj - j)];
+                if (sc >= 0) {
+                    stop_cell = sc;
+                    break;
                 }
-                if (j > 0 && stop_cell == cur) {  // next seed sits in the same cell: this chunk is empty
-                    endcode = END_HANDOFF;
-                    mode = MODE_DONE;
-                }
-                if (limit <= 0) {  // while i < MAX_ITER never runs
-                    endcode = END_CAP;
-                    mode = MODE_DONE;
-                }
+            }
+            if (j > 0 && stop_cell == cur) {  // next seed sits in the same cell: this chunk is empty
+                endcode = END_HANDOFF;
+                mode = MODE_DONE;
+            }
+            if (limit <= 0) {  // while i < MAX_ITER never runs
+                endcode = END_CAP;
+                mode = MODE_DONE;
             }
         }
     }
@@ -197,29 +182,11 @@ __global__ void __launch_bounds__(kTopoThreads, RT_TOPO_MIN_BLOCKS) k_topo(const
                 }
             }
         }
-        if (FILL) {
-            long long o = out + nseg;
-            int k = (int)(o & 7);
-            s_rec[k * kTopoThreads + tid] = rec;
-            bool last = nseg + 1 >= limit;
-            if (k == 7 || last) {
-                long long g0 = o & ~7LL;
-                int kf = (int)((g0 > out ? g0 : out) - g0);
-                if (kf == 0 && k == 7) {
-                    int v[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] = s_rec[q * kTopoThreads + tid];
-                    stg256_stream_i(P.rec + g0, pol_stream, v);
-                } else {
-                    for (int kk = kf; kk <= k; ++kk) P.rec[g0 + kk] = s_rec[kk * kTopoThreads + tid];
-                }
-            }
-        }
         nseg += 1;
-        if (nseg >= limit) {  // while i < MAX_ITER (src/track.jl:119) / this chunk's final count in the fill pass
+        if (nseg >= limit) {  // while i < MAX_ITER (src/track.jl:119)
             endcode = END_CAP;
             mode = MODE_DONE;
-        } else if (!FILL && e == stop_cell) {
+        } else if (e == stop_cell) {
             endcode = END_HANDOFF;
             mode = MODE_DONE;
         }
@@ -303,17 +270,6 @@ __global__ void __launch_bounds__(kTopoThreads, RT_TOPO_MIN_BLOCKS) k_topo(const
             }
             if (o.code == 0) {
                 n_litpush++;
-                if (FILL) {  // the literal chord is already known: write the Segment now, k_eval skips this record
-                    const long long so = out + nseg;
-                    P.opx[so] = o.px;
-                    P.opy[so] = o.py;
-                    P.oqx[so] = o.qx;
-                    P.oqy[so] = o.qy;
-                    P.olen[so] = o.l;
-                    P.oelem[so] = o.e + 1;
-                    if (P.vol) atomicAdd(&P.vol[o.e], P.ang.delta_eff[az] * o.l);
-                    if (P.tsum) atomicAdd(&P.tsum[t], o.l);
-                }
                 push(o.e, (o.e << 2) | 1);
                 cur = o.e;
                 cur_kout = o.e_q;
@@ -336,7 +292,7 @@ __global__ void __launch_bounds__(kTopoThreads, RT_TOPO_MIN_BLOCKS) k_topo(const
         int *dst = P.pool + (long long)pb * kRecBlock + (((nseg - 1) & (kRecBlock - 1)) - (rem - 1));
         for (int kk = 0; kk < rem; ++kk) dst[kk] = s_rec[kk * kTopoThreads + tid];
     }
-    if (!FILL && t < P.n_tracks && j < P.ch.nch[t]) {
+    if (t < P.n_tracks && j < P.ch.nch[t]) {
         P.ch.count[cidx] = active ? nseg : 0;
         P.ch.sum[cidx] = 0.0;
         P.ch.endcode[cidx] = active ? (endcode | (status << 8)) : (END_HANDOFF | (0 << 8));
@@ -348,7 +304,7 @@ __global__ void __launch_bounds__(kTopoThreads, RT_TOPO_MIN_BLOCKS) k_topo(const
     }
 }
 
-// ---- stage 2 of the fill pass: one thread per segment --------------------------------------------------------------------
+// ---- per-track length check after the fill --------------------------------------------------------------------------------
 struct EvalParams {
     DevMesh m;
     TrackSoA t;
@@ -358,7 +314,6 @@ struct EvalParams {
     long long trk_begin, trk_end;  // tracks of this batch
     long long offset_base;         // offsets[trk_begin]
     long long n_seg;               // segments of this batch
-    const int *rec;
     double *opx, *opy, *oqx, *oqy, *olen;
     int *oelem;
     double *vol;

@@ -71,9 +71,8 @@ struct WalkParams {
     int *oelem;
     double *vol;                   // unnormalised sum(delta_eff*len) per element, or nullptr
     unsigned long long *counters;  // [fast transitions, literal iterations, nn queries, knn queries] or nullptr
-    int *rec;                      // two-stage pipeline (topo.cuh): per-segment records
     int *verify_fail;
-    double *tsum;                  // two-stage pipeline: per-track sum of segment lengths
+    double *tsum;                  // self-verifying pipelines: per-track sum of segment lengths
     // single-walk pipeline (k_topo<2> + k_eval3): pool of record blocks
     int *pool;                     // pool_blocks * kRecBlock records
     int *pool_next;                // per block: the chunk's next block

@@ -83,6 +83,7 @@ def init_comm(tg, group=None) -> None:
         _lib.check(tg._ctx, L.rt_comm_unique_id(tg._ctx, buf))
     ident = broadcast_bytes(buf.raw if rank == 0 else None, 128, group)
     _lib.check(tg._ctx, L.rt_comm_init(tg._ctx, world, rank, ident))
+    tg._has_comm = True
 
 
 def shard_range(tg, rank: int, n_ranks: int):

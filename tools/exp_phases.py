@@ -40,12 +40,7 @@ def run(label, flags=0, reps=3, **opts):
 
 run("default (hybrid)")
 print("fallbacks", tg.info("verify_fallbacks"))
-run("two-stage", pipeline=2)
-print("eval_ms", tg.info("eval_ms"), "fallbacks", tg.info("verify_fallbacks"))
 if os.environ.get("RT_EXP_MIN"):
-    for w in (2, 4, 8):
-        run(f"two-stage eval_waves={w}", pipeline=2, eval_waves=w)
-        print("eval_ms", tg.info("eval_ms"))
     sys.exit(0)
 run("sequential", rt.RT_SEG_SEQUENTIAL)
 if os.environ.get("RT_EXP_QUICK"):

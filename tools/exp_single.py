@@ -50,7 +50,6 @@ if small:
 c3t = run("single-walk (3), k_topo<2>", pipeline=3, march=0, chk=small)
 if small:
     print("checksums equal:", c0 == c3t, flush=True)
-run("two-stage (2)", pipeline=2)
 for cs in (64, 96, 192, 256):
     run(f"single-walk chunk={cs}", pipeline=3, chunk_segments=cs)
 for og in (0, 16, 64):
