@@ -4,14 +4,17 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg2|cfg4|cfg5|pincell] [--impl ours|reference]
 
 A "step" is one pass of the hot path over the workload's tracks with mesh + tracks already resident in
-HBM: count pass -> scan -> fill pass (+ fused per-element volumes) -> volumes normalise (+ NCCL all-reduce
-when N > 1).  The default workload is BASELINE.json configs[2] (unit square, ~1.0 M jittered triangles,
-n_phi = 64, delta = 1e-3), the largest named configuration whose 2.2 GB of segments fit one GPU without
-batching.  For N > 1 the tracks are sharded by uid range (mesh replicated) and the track spacing is
-delta / N, so per-GPU work stays fixed ("scaling": "weak").  `e2e` is the same metric through the host API
-with HOST buffers: mesh upload (H2D) + trace! + segmentize! + download of every Segment record (D2H).
-`--impl reference` times the reference's CPU algorithm (the oracle port: Julia is not installable here)
-on all host cores over a bounded uid sample of the same workload.
+HBM: walk (count + record) -> scan -> evaluation (+ fused per-element volumes) -> volumes normalise (+ NCCL
+all-reduce when N > 1).  The default workload is BASELINE.json configs[2] (unit square, ~1.0 M jittered
+triangles, n_phi = 64, delta = 1e-3), the largest named configuration whose 2.2 GB of segments fit one GPU
+without batching.  For N > 1 the tracks are sharded by uid range (mesh replicated) and the track spacing is
+delta / N, so per-GPU work stays fixed ("scaling": "weak"); the same line then carries a `strong` block: the
+named configs[3] (cfg4) -- and configs[4] (cfg5) at N = 8 -- sharded at their named sizes, with the
+unsharded single-GPU time measured in the same run.  `e2e` is the same metric through the host API with HOST
+buffers: mesh upload (H2D) + trace! + segmentize! + download of every Segment record (D2H).  `parity`
+compares the GPU's segments of sampled uid blocks with the CPU oracle, bit for bit, in the same run.
+`--impl reference` times the reference's CPU algorithm (the oracle port: Julia is not installable here) on
+all host cores over a bounded uid sample of the same workload.
 """
 import argparse
 import json
@@ -29,6 +32,7 @@ sys.path.insert(0, ROOT)
 # segmentize!(tg; rtol): with the default rtol = sqrt(eps) the reference's own length check (src/track.jl:171-175) throws on 88
 # corner tracks of cfg3 (it drops a 2e-8 chord); 1e-6 -- the remedy its error message suggests -- lets every track complete.
 RTOL = 1e-6
+SEG_KEYS = ("px", "py", "qx", "qy", "len", "element")
 
 
 def load_workload(name, n_gpus, strong=False):
@@ -118,28 +122,79 @@ class ClockSampler:
                 "samples": len(sm), "how": self.how}
 
 
-def cpu_sample(model, n_azim, delta, budget_segments=3.0e7, blocks=16, threads=None):
-    """Reference CPU algorithm (oracle port) over `blocks` uid ranges spread evenly over the workload."""
+# ---- the CPU side: reference algorithm (oracle port) on sampled uid blocks, timed and -- optionally -- compared with the GPU ------
+class Compare:
+    """What the GPU produced for this rank's shard, on the host: offsets / status of the shard's tracks and the Segment columns
+    of the resident batch (the whole shard for the benched workloads).  `check(otg, u0, u1)` compares one oracle block."""
+
+    def __init__(self, tg, seg):
+        self.uid_begin, self.uid_end = tg.uid_begin, tg.uid_end
+        self.off, self.status, self.seg = tg.segment_offsets, tg.segment_status, seg
+        self.res = tg.resident_batch()
+        self.tracks = self.segments = self.mismatches = 0
+        self.first = None
+
+    def check(self, otg, u0, u1):
+        lo_u, hi_u = max(u0, self.uid_begin, self.res[0]), min(u1, self.uid_end, self.res[1])
+        if hi_u <= lo_u:
+            return
+        o = otg.fetch(lo_u, hi_u)
+        a, b = lo_u - self.uid_begin, hi_u - self.uid_begin
+        bad = 0
+        if not np.array_equal(np.diff(self.off[a:b + 1]), o["counts"]):
+            bad += int(np.count_nonzero(np.diff(self.off[a:b + 1]) != o["counts"]))
+        elif not np.array_equal(self.status[a:b], o["status"]):
+            bad += int(np.count_nonzero(self.status[a:b] != o["status"]))
+        else:
+            s0, s1 = int(self.off[a] - self.res[2]), int(self.off[b] - self.res[2])
+            for k in SEG_KEYS:  # bit-exact: element ids and order, p / q / len
+                g = self.seg[k][s0:s1]
+                if not np.array_equal(g, o[k]):
+                    bad += int(np.count_nonzero(g != o[k]))
+        if bad and self.first is None:
+            self.first = f"uids [{lo_u}, {hi_u})"
+        self.mismatches += bad
+        self.tracks += hi_u - lo_u
+        self.segments += int(o["counts"].sum())
+
+    def result(self):
+        return {"checked_tracks": int(self.tracks), "checked_segments": int(self.segments), "mismatches": int(self.mismatches),
+                "ok": bool(self.mismatches == 0 and self.segments > 0), "first_mismatch": self.first,
+                "what": "GPU vs CPU oracle on sampled uid blocks: per-track counts and status, element ids and order, p/q/len bit for bit"}
+
+
+def estimate_segments(model, mesh, n_azim, delta):
+    return (mesh.width * mesh.height) * (n_azim / 2) / delta / (0.45 * (2 * mesh.width * mesh.height / model.num_cells) ** 0.5)
+
+
+def cpu_sample(model, n_azim, delta, budget_segments=3.0e7, blocks=16, threads=None, compare=None, uid_range=None, otg=None):
+    """Reference CPU algorithm (oracle port) over `blocks` uid ranges spread evenly over [uid_range) of the workload.
+    Only orc_segmentize is timed; fetching and comparing the blocks (compare) is not."""
     import raytracing_jl_b200 as rt
     from oracle.oracle import OracleMesh, OracleTrackGenerator
 
     threads = threads or os.cpu_count() or 1
     mesh = rt.Mesh(model)
-    otg = OracleTrackGenerator(OracleMesh.from_mesh(mesh), n_azim, delta, bcs=(1, 1, 1, 1)).trace()
-    n = otg.n_total_tracks
-    est_total = (mesh.width * mesh.height) * (n_azim / 2) / delta / (0.45 * (2 * mesh.width * mesh.height / model.num_cells) ** 0.5)
-    frac = min(1.0, budget_segments / max(est_total, 1.0))
+    if otg is None:
+        otg = OracleTrackGenerator(OracleMesh.from_mesh(mesh), n_azim, delta, bcs=(1, 1, 1, 1)).trace()
+    lo, hi = uid_range or (1, otg.n_total_tracks + 1)
+    n = hi - lo
+    frac = min(1.0, budget_segments / max(estimate_segments(model, mesh, n_azim, delta) * n / otg.n_total_tracks, 1.0))
+    blocks = max(1, min(blocks, n))
     per = max(1, int(n * frac / blocks))
     segs, secs = 0, 0.0
     for b in range(blocks):
-        u0 = 1 + int(b * (n - per) / max(blocks - 1, 1)) if frac < 1.0 else 1 + b * (n // blocks)
-        u1 = u0 + per if frac < 1.0 else (n + 1 if b == blocks - 1 else 1 + (b + 1) * (n // blocks))
+        u0 = lo + int(b * (n - per) / max(blocks - 1, 1)) if frac < 1.0 else lo + b * (n // blocks)
+        u1 = u0 + per if frac < 1.0 else (hi if b == blocks - 1 else lo + (b + 1) * (n // blocks))
         t0 = time.perf_counter()
         otg.segmentize(rtol=RTOL, uid_begin=u0, uid_end=u1, nthreads=threads, fetch=False, check=False)
         secs += time.perf_counter() - t0
         segs += otg.n_segments
+        if compare is not None:
+            compare.check(otg, u0, u1)
         otg.free_segments()
-    return segs, secs, threads, f"{blocks} uid blocks x {per} tracks = {100 * min(1.0, blocks * per / n):.1f}% of {n} tracks"
+    sample = f"{blocks} uid blocks x {per} tracks = {100 * min(1.0, blocks * per / otg.n_total_tracks):.1f}% of {otg.n_total_tracks} tracks"
+    return segs, secs, threads, sample, otg
 
 
 def run_reference(args):
@@ -148,20 +203,26 @@ def run_reference(args):
         return
     model, n_azim, delta = load_workload(args.workload, args.gpus, args.strong)
     threads = os.cpu_count() or 1
-    budget = 2.0e7 / max(1, args.steps + args.warmup) * 3
-    tot_s, tot_t, sample = 0, 0.0, ""
+    # every step is a bounded sample of the workload, in FEW LARGE blocks so that every host thread has many tracks to walk
+    # (schedule(dynamic, 1) over >= 64 tracks per thread); 1e7 - 3e7 segments per step keep the whole run within a minute
+    budget = min(3.0e7, max(1.0e7, 2.5e8 / max(1, args.steps + args.warmup)))
+    tot_s, tot_t, sample, otg = 0, 0.0, "", None
     for it in range(args.warmup + args.steps):
-        s, t, threads, sample = cpu_sample(model, n_azim, delta, budget_segments=budget, threads=threads)
+        s, t, threads, sample, otg = cpu_sample(model, n_azim, delta, budget_segments=budget, blocks=4, threads=threads, otg=otg)
         if it >= args.warmup:
             tot_s += s
             tot_t += t
     v = tot_s / tot_t
+    # the reference's own execution model is ONE thread (src/trackgenerator.jl:362): a smaller sample, reported next to it
+    s1, t1, _, sample1, otg = cpu_sample(model, n_azim, delta, budget_segments=3.0e6, blocks=4, threads=1, otg=otg)
     out = {"impl": "reference", "metric": "segments/sec for segmentize!", "value": v, "unit": "segments/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": workload_config(args, model, n_azim, delta),
            "cpu_baseline": {"value": v, "unit": "segments/s", "cores": threads, "kind": "port",
-                            "sample": sample + " per step; OpenMP over tracks (the reference itself is serial)"},
+                            "sample": sample + " per step; OpenMP over tracks, schedule(dynamic, 1) (the reference itself is serial)"},
+           "cpu_baseline_1thread": {"value": s1 / t1, "unit": "segments/s", "cores": 1, "kind": "port", "sample": sample1,
+                                    "note": "the reference's own execution model: one serial loop over tracks_by_uid"},
            "e2e": {"value": v, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -175,6 +236,64 @@ def workload_config(args, model, n_azim, delta):
             "l2": "inputs larger than L2: cell+edge records 160 B/cell and >2 GB of segment output stream through the 126 MB L2 every step"}
 
 
+def strong_block(name, rank, world, local, dist, torch, steps=3):
+    """The named workload `name` at its named size: first unsharded on every GPU (N independent replicas = the 1-GPU time, max
+    over ranks), then sharded by uid range over the N GPUs with the volume all-reduce.  Device time between two events on the
+    library's stream, max over ranks."""
+    import raytracing_jl_b200 as rt
+    from raytracing_jl_b200.distributed import init_comm
+
+    model, n_azim, delta = rt.synth.workload(name)
+    mesh = rt.Mesh(model)
+    bcs = rt.BoundaryConditions(top=rt.Reflective, bottom=rt.Reflective, right=rt.Reflective, left=rt.Reflective)
+    area = rt.synth.mesh_area(model)
+
+    def timed(tg, k):
+        rt.segmentize_(tg, rtol=RTOL, check=False, fetch_volumes=False)  # warm-up (allocations, first-touch)
+        dist.barrier()
+        torch.cuda.synchronize()
+        tg.timer_start()
+        ph = []
+        for _ in range(k):
+            rt.segmentize_(tg, rtol=RTOL, check=False, fetch_volumes=False)
+            ph.append(tg.phase_ms())
+        ms = tg.timer_stop() / k
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        walk = torch.tensor([float(np.mean([p["count"] for p in ph]))], dtype=torch.float64, device="cuda")
+        ws = [torch.zeros_like(walk) for _ in range(world)]
+        dist.all_gather(ws, walk)
+        return float(t.item()), [float(w.item()) for w in ws]
+
+    out = {"workload": name, "n_cells": int(model.num_cells), "n_azim": n_azim, "delta": delta, "steps": steps}
+    one = None
+    if name != "cfg5":  # (cfg5 unsharded takes ~9 s per step on one GPU; its 1-GPU time is not part of the default run)
+        tg1 = rt.TrackGenerator(mesh, n_azim, delta, bcs=bcs, device=local)
+        rt.trace_(tg1)
+        one, _ = timed(tg1, max(1, steps - 1))
+        out["segments"] = int(tg1.n_segments)
+        out["ms_per_step_1gpu"] = one
+        tg1.close()
+        del tg1
+    tg = rt.TrackGenerator(mesh, n_azim, delta, bcs=bcs, device=local, shard=(rank, world))
+    init_comm(tg)
+    rt.trace_(tg)
+    ms, walks = timed(tg, steps)
+    rt.segmentize_(tg, rtol=RTOL, check=False)  # (fetches the all-reduced volumes)
+    tg.segment_offsets  # (also fetches tg.segment_status)
+    n = torch.tensor([float(tg.n_segments), float(np.count_nonzero(tg.segment_status))], dtype=torch.float64, device="cuda")
+    dist.all_reduce(n)
+    nseg = int(n[0].item())
+    out.update({"value": nseg / (ms * 1e-3), "unit": "segments/s", "ms_per_step": ms, "segments_sharded": nseg, "bad_tracks": int(n[1].item()),
+                "walk_ms_per_rank": walks, "walk_spread": (max(walks) - min(walks)) / max(float(np.mean(walks)), 1e-9),
+                "volumes_sum_over_area": float(tg.volumes.sum() / area)})
+    if one is not None:
+        out["efficiency_vs_n1"] = one / (world * ms)
+        out["segments_match_unsharded"] = bool(nseg == out["segments"])
+    tg.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -184,6 +303,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-strong-block", action="store_true", help="N > 1: skip the cfg4 (and, at N = 8, cfg5) strong-scaling block")
     ap.add_argument("--clock-period-ms", type=float, default=20.0)
     ap.add_argument("--strong", action="store_true", help="N > 1: shard the named workload itself (fixed total work) instead of delta / N")
     ap.add_argument("--pipeline", type=int, default=None, help="rt_set_option('pipeline'): 0 hybrid, 1 sequential, 3 single-walk")
@@ -201,7 +321,6 @@ def main():
     import torch.distributed as dist
 
     import raytracing_jl_b200 as rt
-    from raytracing_jl_b200 import _lib
     from raytracing_jl_b200.distributed import init_comm
 
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -254,31 +373,36 @@ def main():
         break
     nseg_local = tg.n_segments
     st = tg.stats()
+    tg.segment_offsets  # (also fetches tg.segment_status)
     if world > 1:
         print(f"[rank {rank}] ms/step {ms / args.steps:.3f} segments {nseg_local} phases "
               f"{ {k: round(float(np.mean([p[k] for p in phases])), 3) for k in phases[0]} }", file=sys.stderr)
     t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    n_all = torch.tensor([float(nseg_local), float(tg.uid_end - tg.uid_begin)], dtype=torch.float64, device="cuda")
+    n_all = torch.tensor([float(nseg_local), float(tg.uid_end - tg.uid_begin), float(np.count_nonzero(tg.segment_status))],
+                         dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(n_all, op=dist.ReduceOp.SUM)
     ms_max = float(t_ms.item())
-    nseg, ntrk = float(n_all[0].item()), float(n_all[1].item())
+    nseg, ntrk, nbad = float(n_all[0].item()), float(n_all[1].item()), int(n_all[2].item())
     value = nseg * args.steps / (ms_max * 1e-3)
 
-    # ---- roofline of the dominant kernel (the fill pass k_walk<true>): SURVEY 8(d) algorithmic bytes per launch
+    # ---- roofline: SURVEY 8(d) algorithmic bytes per launch; `frac` = the dominant kernel (the evaluation), `frac_step` = the
+    # whole step (count + scan + fill + volumes, host gaps included: the timed region itself)
     fill_ms = float(np.mean([p["fill"] for p in phases]))
     count_ms = float(np.mean([p["count"] for p in phases]))
     alg_bytes = 44.0 * nseg_local + 72.0 * (tg.uid_end - tg.uid_begin) + 40.0 * model.num_cells
     peak, peak_src = peaks()
     achieved = alg_bytes / (fill_ms * 1e-3) / 1e9
+    achieved_step = alg_bytes / (ms / args.steps * 1e-3) / 1e9
     kern = {3: "k_eval3 (one lane per segment: records -> Segment columns)", 0: "k_walk<true> (fill pass)",
             1: "k_walk<true> (fill pass)"}[3 if args.pipeline is None else args.pipeline]
     roofline = {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                "launch_ms": fill_ms, "count_pass_ms": count_ms,
-                "note": "launch_ms = the fill phase (dominant kernel + k_track_status); the count walk (k_march) is a latency-bound "
-                        "pointer chase with ~4 algorithmic bytes per segment, see DESIGN.md and profiles/"}
+                "launch_ms": fill_ms, "count_pass_ms": count_ms, "achieved_step": achieved_step, "frac_step": achieved_step / peak,
+                "note": "frac: launch_ms = the fill phase (dominant kernel + k_track_status); frac_step: the same algorithmic bytes over the "
+                        "whole step (SURVEY 8d: count + scan + fill + volumes).  The count walk (k_march) is a latency-bound pointer chase "
+                        "with ~4 algorithmic bytes per segment, see DESIGN.md and profiles/"}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
@@ -287,7 +411,7 @@ def main():
             pass
 
     # ---- e2e through the public API with host buffers
-    e2e = None
+    e2e, seg = None, None
     if not args.no_e2e:
         def e2e_step():
             tg.upload_mesh()  # H2D of the flattened model + device preparation
@@ -314,21 +438,72 @@ def main():
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(dt.item()) / n_e2e,
                "what": "rt_mesh_upload + rt_trace + rt_segmentize + rt_volumes + rt_segment_offsets + rt_segments_download"}
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        s, t, cores, sample = cpu_sample(model, n_azim, delta)
+    # ---- parity in the same run: the GPU's records of sampled uid blocks against the CPU oracle, bit for bit; at N = 1 the sample
+    # is the one the cpu_baseline is timed on, at N > 1 every rank checks a few small blocks of its own shard
+    if seg is None:
+        rt.segmentize_(tg, rtol=RTOL, check=False)
+        seg = tg.fetch_segments()
+    cmp_ = Compare(tg, seg)
+    cpu = cpu1 = None
+    if world == 1 and not args.no_cpu_baseline:
+        s, t, cores, sample, otg = cpu_sample(model, n_azim, delta, compare=cmp_)
         cpu = {"value": s / t, "unit": "segments/s", "cores": cores, "kind": "port", "sample": sample,
-               "note": "oracle port of the reference algorithm, OpenMP over tracks; the Julia reference itself is single-threaded"}
+               "note": "oracle port of the reference algorithm, OpenMP over tracks (schedule(dynamic, 1)); the Julia reference itself is single-threaded"}
+        s1, t1, _, sample1, otg = cpu_sample(model, n_azim, delta, budget_segments=3.0e6, blocks=4, threads=1, otg=otg)
+        cpu1 = {"value": s1 / t1, "unit": "segments/s", "cores": 1, "kind": "port", "sample": sample1,
+                "note": "the reference's own execution model: one serial loop over tracks_by_uid (src/trackgenerator.jl:362)"}
+    else:
+        cpu_sample(model, n_azim, delta, budget_segments=4.0e5, blocks=4, compare=cmp_, uid_range=(tg.uid_begin, tg.uid_end))
+    parity = cmp_.result()
+    area = rt.synth.mesh_area(model)
+    rt.segmentize_(tg, rtol=RTOL, check=False)  # (fetches the -- all-reduced -- volumes)
+    parity["volumes_sum_over_area"] = float(tg.volumes.sum() / area)
+    vol_ok = abs(parity["volumes_sum_over_area"] - 1.0) <= 1e-8 or nbad > 0
+    if world > 1:
+        pt = torch.tensor([float(parity["checked_tracks"]), float(parity["checked_segments"]), float(parity["mismatches"])],
+                          dtype=torch.float64, device="cuda")
+        dist.all_reduce(pt)
+        parity.update(checked_tracks=int(pt[0].item()), checked_segments=int(pt[1].item()), mismatches=int(pt[2].item()))
+        # every rank holds the same all-reduced volumes, bit for bit
+        v = torch.tensor(tg.volumes, device="cuda")
+        lo, hi = v.clone(), v.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        parity["ranks_hold_identical_volumes"] = bool(torch.equal(lo, hi))
+        # the shards' segments add up to the unsharded count (rank 0 counts the whole track set with the sequential kernels)
+        parity["segments_match_unsharded"] = None
+        if rank == 0:
+            whole = rt.TrackGenerator(mesh, n_azim, delta, bcs=bcs, device=local)
+            rt.trace_(whole)
+            rt.segmentize_(whole, rtol=RTOL, check=False, flags=rt.RT_SEG_COUNT_ONLY | rt.RT_SEG_NO_VOLUMES)
+            parity["segments_unsharded"] = int(whole.n_segments)
+            parity["segments_match_unsharded"] = bool(int(whole.n_segments) == int(nseg))
+            whole.close()
+        parity["ok"] = bool(parity["mismatches"] == 0 and parity["checked_segments"] > 0 and parity["ranks_hold_identical_volumes"]
+                            and vol_ok and parity["segments_match_unsharded"] is not False)
+    else:
+        parity["ok"] = bool(parity["ok"] and vol_ok)
+    launches = int(st["launches"] + 1) * args.steps
+    fallbacks = int(tg.info("verify_fallbacks"))
+    bad_status = int(tg.bad_status)
+
+    # ---- strong scaling at the named sizes (N > 1): cfg4 sharded vs unsharded in the same run, cfg5 at N = 8
+    strong = None
+    if world > 1 and not args.no_strong_block and not args.strong and args.workload == "cfg3":
+        tg.close()
+        strong = strong_block("cfg4", rank, world, local, dist, torch)
+        if world >= 8:
+            strong["cfg5"] = strong_block("cfg5", rank, world, local, dist, torch, steps=2)
 
     if rank == 0:
         out = {"metric": "segments/sec for segmentize!", "value": value, "unit": "segments/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, model, n_azim, delta),
-               "segments_per_step": nseg, "tracks": ntrk, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-               "gpu_launches": int(st["launches"] + 1) * args.steps,
+               "segments_per_step": nseg, "tracks": ntrk, "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_1thread": cpu1,
+               "e2e": e2e, "parity": parity, "strong": strong, "clocks": clocks, "gpu_launches": launches,
                "phase_ms": {k: float(np.mean([p[k] for p in phases])) for k in phases[0]},
                "walk_stats": {k: st[k] for k in ("fast_transitions", "literal_iterations", "nn_queries", "knn_queries")},
-               "bad_tracks_status": int(tg.bad_status), "retimed": retimed, "verify_fallbacks": int(tg.info("verify_fallbacks"))}
+               "bad_tracks": nbad, "bad_tracks_status": bad_status, "retimed": retimed, "verify_fallbacks": fallbacks}
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(out), flush=True)

@@ -216,6 +216,16 @@ class OracleTrackGenerator:
             raise OracleError(f"track uid {bad.value}: {STATUS.get(rc, rc)}")
         return self
 
+    def fetch(self, uid_begin: int, uid_end: int):
+        """counts / status / Segment columns of the already segmentized uids [uid_begin, uid_end), concatenated in uid order"""
+        nt = uid_end - uid_begin
+        out = dict(counts=np.zeros(nt, np.int64), status=np.zeros(nt, np.int32))
+        lib().orc_seg_counts(self._h, uid_begin, uid_end, out["counts"], out["status"])
+        S = int(out["counts"].sum())
+        out.update(px=np.zeros(S), py=np.zeros(S), qx=np.zeros(S), qy=np.zeros(S), len=np.zeros(S), element=np.zeros(S, np.int32))
+        lib().orc_seg_copy(self._h, uid_begin, uid_end, *[out[k].ctypes.data_as(C.c_void_p) for k in ("px", "py", "qx", "qy", "len", "element")])
+        return out
+
     def stats(self):
         s = np.zeros(8, np.int64)
         lib().orc_seg_stats(self._h, s)

@@ -43,6 +43,16 @@ for rep in range(5):
 n = torch.tensor([float(tg.n_segments)], device="cuda", dtype=torch.float64)
 dist.all_reduce(n)
 assert int(n.item()) == ref.n_segments, (int(n.item()), ref.n_segments)
+# a rank whose rt_segmentize fails still joins the collective (zero contribution + failed-rank flag): nobody hangs, the failing
+# rank raises its own error and its peers are told that the sums are incomplete (RT_ERR_PEER)
+try:
+    rt.segmentize_(tg, rtol=1e-6, check=False, k=(33 if rank == world - 1 else 5))  # k > RT_MAX_K: RT_ERR_ARG on the last rank only
+    raised = None
+except rt.RTError as e:
+    raised = e.code
+assert raised == (-2 if rank == world - 1 else -11), raised
+rt.segmentize_(tg, rtol=1e-6, check=False)  # ... and the next call is clean again
+assert np.allclose(tg.volumes, vref, rtol=1e-10, atol=0.0)
 if rank == 0:
     print(f"nccl volumes ok: {world} ranks, {ref.n_segments} segments, sum(vol)/area = {vref.sum() / area:.12f}", flush=True)
 dist.destroy_process_group()
