@@ -387,9 +387,15 @@ class TrackGenerator(TrackLayout):
                 raise RuntimeError("call segmentize_ first")
             n = self.uid_end - self.uid_begin
             self._offsets = np.zeros(n + 1, np.int64)
-            self.segment_status = np.zeros(n, np.int32)
-            _lib.check(self._ctx, _lib.lib().rt_segment_offsets(self._ctx, _lib.ptr(self._offsets), _lib.ptr(self.segment_status)))
+            self._status = np.zeros(n, np.int32)
+            _lib.check(self._ctx, _lib.lib().rt_segment_offsets(self._ctx, _lib.ptr(self._offsets), _lib.ptr(self._status)))
         return self._offsets
+
+    @property
+    def segment_status(self):
+        """per-track status of the last segmentize_ (RT_TRACK_*: 0 ok, 1 "Try increasing k", 2 length check, 4 undefined x_int)"""
+        self.segment_offsets
+        return self._status
 
     @property
     def segments(self):
