@@ -316,6 +316,14 @@ __global__ void __launch_bounds__(kMarchThreads, RT_MARCH_MIN_BLOCKS) k_march(co
     unsigned diag_tot = 0, diag_done = 0, diag_wait = 0;  // lane-slots of the fast loop: all / finished lanes / lanes waiting for the slow side
 #endif
 
+    // The record of the half-edge to enter next (apex, twins of the two possible exit edges, clearances) is REQUESTED AS SOON AS
+    // THE EXIT EDGE IS KNOWN -- two multiply-adds and a sign test after the previous record arrived -- and lands while the rest of
+    // the transition (clearance and cheap-filter tests, record staging, end conditions) executes: the walk is one dependent gather
+    // per step, so every instruction between "record arrived" and "next record requested" is latency the next step pays for
+    // (profiles/r1_w: 32 % of the walk's stall samples sat on this load, behind ~80 instructions of bookkeeping).
+    double rax = 0.0, ray = 0.0, rw0 = 0.0, rw1 = 0.0;
+    if (mode == MODE_FAST && enc >= 0) ldg256_keep(m.he + (enc >> 3), pol_keep, rax, ray, rw0, rw1);
+
     while (__any_sync(FULL, mode != MODE_DONE)) {
         // ------------------------------------------------------------------ FAST phase: sign tests only
 #pragma unroll 1
@@ -330,43 +338,49 @@ __global__ void __launch_bounds__(kMarchThreads, RT_MARCH_MIN_BLOCKS) k_march(co
             else if (mode != MODE_FAST) diag_wait++;
 #endif
             if (mode != MODE_FAST) continue;
-            bool ok = false;
-            if (enc >= 0) {
-                double ax, ay, w0, w1;
-                ldg256_keep(m.he + (enc >> 3), pol_keep, ax, ay, w0, w1);
-                const float clearf = __int_as_float(__double2loint(w1));
-                const float clearB = fabsf(clearf);
-                const double sa = ta * ax + tb * ay + tc;
-                const double thr = g * (double)fmaxf(clearA, clearB);
-                if ((fabs(sa) >= thr) && (fabs(s1) >= thr) && (fabs(s2) >= thr)) {
-                    const bool opp1 = (sa > 0) != (s1 > 0);  // the exit edge joins the apex with the end point across the line
-                    const double ks = opp1 ? s1 : s2;        // ... which is the only vertex on its side of the track line
-                    const bool exit1 = (opp1 == (f != 0));
-                    const int nenc = exit1 ? __double2loint(w0) : __double2hiint(w0);
-                    const float clear2 = __int_as_float(__double2hiint(w1));
-                    // cheap filter: the geometric fast-path conditions hold without evaluating the chord; transitions
-                    // it cannot decide (and every cell of the bounding-box band) are re-examined exactly by march_slow
-                    // cheap filter: the geometric fast-path conditions hold without evaluating the chord; transitions
-                    // it cannot decide (and every cell of the bounding-box band) are re-examined exactly by march_slow -- not
-                    // here: any call or any larger body inside this loop makes ptxas keep the walker's state in local memory
-                    const bool accept = cheap_ok && (clearf >= 0.0f) && (fabs(ks) >= g * (double)clear2) && (fabs(ks) + fabs(sa) >= ang_thr) &&
-                                        (fabs(s1) + fabs(s2) >= ang_thr);
-                    if (accept) {
-                        const int h = enc >> 3;
-                        last_rec = (h << 2) | (exit1 ? 2 : 0);
-                        s1 = ks;
-                        s2 = sa;
-                        f = (exit1 == ((nenc & 1) != 0)) ? 1 : 0;
-                        enc = nenc;
-                        clearA = clearB;
-                        ok = true;
-                        // (cell of h == stop_cell) without dividing: h in [3*stop_cell, 3*stop_cell + 2]; stop_cell = -1: never
-                        const bool at_stop = (unsigned)(h - 3 * stop_cell) < 3u;
-                        march_push(P, at_stop, last_rec, nseg, pb, recording, mode, endcode, limit, my_rec);
-                    }
-                }
+            if (enc < 0) {  // the exit edge lies on the boundary: the literal walk ends the track
+                mode = MODE_RETRY;
+                continue;
             }
-            if (!ok) mode = MODE_RETRY;
+            const double sa = ta * rax + tb * ray + tc;
+            const bool opp1 = (sa > 0) != (s1 > 0);  // the exit edge joins the apex with the end point across the line
+            const bool exit1 = (opp1 == (f != 0));
+            const int nenc = exit1 ? __double2loint(rw0) : __double2hiint(rw0);
+            const float clearf = __int_as_float(__double2loint(rw1));
+            const float clear2 = __int_as_float(__double2hiint(rw1));
+#ifndef RT_MARCH_LATE_LOAD
+            if (nenc >= 0) ldg256_keep(m.he + (nenc >> 3), pol_keep, rax, ray, rw0, rw1);  // (speculative: the tests below may still say no)
+#endif
+            const float clearB = fabsf(clearf);
+            const double thr = g * (double)fmaxf(clearA, clearB);
+            const double ks = opp1 ? s1 : s2;  // ... which is the only vertex on its side of the track line
+            // clearance test + cheap filter: the geometric fast-path conditions hold without evaluating the chord;
+            // transitions it cannot decide (and every cell of the bounding-box band) are re-examined exactly by march_slow -- not
+            // here: any call or any larger body inside this loop makes ptxas keep the walker's state in local memory
+#ifdef RT_MARCH_BRANCHY
+            const bool accept = (fabs(sa) >= thr) && (fabs(s1) >= thr) && (fabs(s2) >= thr) && cheap_ok && (clearf >= 0.0f) &&
+                                (fabs(ks) >= g * (double)clear2) && (fabs(ks) + fabs(sa) >= ang_thr) && (fabs(s1) + fabs(s2) >= ang_thr);
+#else
+            const bool accept = (fabs(sa) >= thr) & (fabs(s1) >= thr) & (fabs(s2) >= thr) & cheap_ok & (clearf >= 0.0f) &
+                                (fabs(ks) >= g * (double)clear2) & (fabs(ks) + fabs(sa) >= ang_thr) & (fabs(s1) + fabs(s2) >= ang_thr);
+#endif
+            if (!accept) {
+                mode = MODE_RETRY;  // (the record in flight belongs to a half-edge that is not entered: march_slow re-arms)
+                continue;
+            }
+            const int h = enc >> 3;
+            last_rec = (h << 2) | (exit1 ? 2 : 0);
+            s1 = ks;
+            s2 = sa;
+            f = (exit1 == ((nenc & 1) != 0)) ? 1 : 0;
+            enc = nenc;
+            clearA = clearB;
+            // (cell of h == stop_cell) without dividing: h in [3*stop_cell, 3*stop_cell + 2]; stop_cell = -1: never
+            const bool at_stop = (unsigned)(h - 3 * stop_cell) < 3u;
+            march_push(P, at_stop, last_rec, nseg, pb, recording, mode, endcode, limit, my_rec);
+#ifdef RT_MARCH_LATE_LOAD
+            if (mode == MODE_FAST && enc >= 0) ldg256_keep(m.he + (enc >> 3), pol_keep, rax, ray, rw0, rw1);
+#endif
         }
         // ------------------------------------------------------------------ SLOW phase (out of line)
         if (mode == MODE_SLOW || mode == MODE_RETRY) {
@@ -402,6 +416,9 @@ __global__ void __launch_bounds__(kMarchThreads, RT_MARCH_MIN_BLOCKS) k_march(co
             pb = S.pb;
             recording = S.recording;
             endcode = S.endcode;
+            // (assigned on every path: a value that stays live across the call above would be kept in local memory for the whole loop)
+            rax = ray = rw0 = rw1 = 0.0;
+            if (mode == MODE_FAST && enc >= 0) ldg256_keep(m.he + (enc >> 3), pol_keep, rax, ray, rw0, rw1);
         }
     }
 
