@@ -87,6 +87,28 @@ struct rt_ctx {
     DevBuf b_verify, b_tsum;    // self-verifying pipelines: verification flag, per-track length sums
     DevBuf b_pool, b_pool_next, b_pool_cursor;  // single-walk pipeline: record blocks (walk.cuh kRecBlock), chain, cursor
     int count_batches = 0;             // single-walk pipeline: how many uid batches the count walk needed (info)
+    // The chunk plan (k_plan_chunks .. k_unit_scatter) depends on the tracks, the mesh density and the chunk options only: it is
+    // kept between calls and rebuilt when one of them changes (plan_key), so the steady-state segmentize! needs neither its
+    // kernels nor the host round trip that sizes its arrays.
+    unsigned long long trace_gen = 0;  // bumped by rt_trace / rt_mesh_upload
+    struct PlanKey {
+        unsigned long long gen = ~0ULL;
+        double chunk_len = -1.0;
+        int band = -1, order_grid = -1;
+        long long n = -1;
+        bool operator==(const PlanKey &o) const { return gen == o.gen && chunk_len == o.chunk_len && band == o.band && order_grid == o.order_grid && n == o.n; }
+    } plan_key;
+    bool plan_has_order = false;
+    int opt_plan_cache = 1;            // 0: rebuild the chunk plan in every call (test knob)
+    // Optimistic evaluation: when the previous call's Segment columns are still allocated, the evaluation is launched right behind
+    // the walk WITHOUT reading the segment total back first; a one-thread guard kernel compares the total (and the record pool's
+    // cursor) with the capacities on the device and cancels the evaluation if they do not fit -- the host learns it with the
+    // final read-back of the call and repeats the call on the careful path.
+    int opt_optimistic = 1;
+    bool skip_optimistic_once = false;
+    bool deferred_total = false;
+    bool redo_careful = false;         // the repeat asked for by the optimistic path (not a failed verification)
+    DevBuf b_guard;
     int opt_band_chunks = 1;           // 8x shorter chunks for tracks that run along the bounding box (walk.cuh k_plan_chunks)
     int opt_march = 1;                 // single-walk pipeline: k_march (register-resident loop) instead of k_topo<2>
     long long opt_pool_slots = 0;      // test hook: at most this many chunk slots per count batch (0: as many as fit)
@@ -230,7 +252,7 @@ extern "C" void rt_destroy(rt_ctx *ctx) {
                      &ctx->b_scratch, &ctx->b_gcounts,   &ctx->b_gcursor,
                      &ctx->b_omega,   &ctx->b_sigma,     &ctx->b_tau,
                      &ctx->b_pool,    &ctx->b_pool_next, &ctx->b_pool_cursor,
-                     &ctx->b_area,    &ctx->b_factor,    &ctx->b_layout,    &ctx->b_vol_alt};
+                     &ctx->b_area,    &ctx->b_factor,    &ctx->b_layout,    &ctx->b_vol_alt,  &ctx->b_guard};
     for (DevBuf *b : all) release(*b);
     for (int ph = 0; ph < 6; ++ph)
         for (int q = 0; q < 2; ++q)
@@ -405,6 +427,7 @@ extern "C" int rt_mesh_upload(rt_ctx *ctx, int32_t n_nodes, const double *xy, in
     ctx->edge_sum = sc.edge_sum;
     ctx->area = sc.area;
     ctx->clear_tiny = -1.0;
+    ctx->trace_gen++;
     ctx->has_mesh = true;
     ctx->area_valid = false;
     ctx->traced = false;
@@ -574,6 +597,7 @@ extern "C" int rt_trace(rt_ctx *ctx, int32_t n_azim_2, const int64_t *n_tracks_x
         return fail(ctx, RT_ERR_BC_MISMATCH, "Boundaries do not match! (uid %lld)", uid);
     }
     ctx->traced = true;
+    ctx->trace_gen++;
     return RT_OK;
 }
 
@@ -706,6 +730,11 @@ __global__ void k_first_bad(const int *status, long long n, unsigned long long *
 __global__ void k_normalise(const double *in, double *out, int n, double denom) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i] / denom;  // volumes ./= n_azim_2, src/trackgenerator.jl:386
+}
+
+// optimistic evaluation: does the batch fit the Segment columns and did the record pool hold every record?  (one thread)
+__global__ void k_guard(const long long *total_at, long long base, long long cap, const int *pool_cursor, int pool_blocks, int *cancel) {
+    *cancel = (*total_at - base > cap || *pool_cursor > pool_blocks) ? 1 : 0;
 }
 
 extern "C" int rt_set_segment_capacity(rt_ctx *ctx, int64_t max_segments_resident) {
@@ -867,6 +896,55 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
         launches += 6;
         CK(cudaMemcpyAsync(&ctx->h_pin[1], (long long *)ctx->b_offsets.p + e, sizeof(long long), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&ctx->h_pin[9], P.pool_cursor, sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (!multi && !cb && ctx->cap_cfg == 0 && ctx->opt_optimistic && !ctx->skip_optimistic_once && ctx->b_seg_d.p && ctx->cap > 0) {
+            // ---- optimistic evaluation: no host round trip between the walk and the evaluation (see rt_ctx::opt_optimistic)
+            CK(ensure(ctx->b_guard, sizeof(int)));
+            k_guard<<<1, 1, 0, st>>>((const long long *)ctx->b_offsets.p + e, base, ctx->cap, P.pool_cursor, P.pool_blocks, (int *)ctx->b_guard.p);
+            P.opx = ctx->s_px;
+            P.opy = ctx->s_py;
+            P.oqx = ctx->s_qx;
+            P.oqy = ctx->s_qy;
+            P.olen = ctx->s_len;
+            P.oelem = ctx->s_elem;
+            P.vol = want_vol ? ctx->vol_acc : nullptr;
+            P.trk_begin = b;
+            P.trk_end = e;
+            P.offset_base = base;
+            WalkParams PE = P;
+            PE.lmin = lmin_eval;
+            PE.cancel = (const int *)ctx->b_guard.p;
+            tic(ctx, 4);
+            k_eval3<<<blocks_for((PE.unit_end - PE.unit_begin) * 32 * 32, kEval3Threads), kEval3Threads, 0, st>>>(PE);
+            EvalParams E{};
+            E.m = P.m;
+            E.t = ctx->t;
+            E.ang = P.ang;
+            E.offsets = P.offsets;
+            E.n_tracks = n;
+            E.olen = P.olen;
+            E.status = P.status;
+            E.tsum = P.tsum;
+            E.rtol = rtol;
+            E.trk_begin = b;
+            E.trk_end = e;
+            E.offset_base = base;
+            E.cancel = PE.cancel;
+            k_track_status<<<blocks_for(e - b, 128), 128, 0, st>>>(E);
+            launches += 3;
+            CK(cudaGetLastError());
+            toc(ctx, 4);
+            ctx->h_pin[2] = 0;
+            ctx->h_pin[10] = 0;
+            CK(cudaMemcpyAsync(&ctx->h_pin[2], ctx->b_verify.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&ctx->h_pin[10], ctx->b_guard.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            ctx->res_trk_begin = b;
+            ctx->res_trk_end = e;
+            ctx->res_off_base = base;
+            ctx->deferred_total = true;  // total / resident count are filled in by segmentize_once after its final read-back
+            *deferred_verify = true;
+            *launches_io += launches;
+            return RT_OK;
+        }
         CK(cudaStreamSynchronize(st));
         take(2);
         take(3);
@@ -1051,25 +1129,38 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         est_total_segments = est_total;
         double seg_target = fmax(ctx->opt_chunk_segments, est_total / ctx->opt_target_walkers);
         double chunk_len = (flags & RT_SEG_NO_CHUNKS) || !(rho > 0.0) ? INFINITY : seg_target / rho;
-        CK(ensure(ctx->b_nch, sizeof(int) * (size_t)n));
-        CK(ensure(ctx->b_blk_chunks, sizeof(int) * (size_t)n_blocks));
-        CK(ensure(ctx->b_unit_base, sizeof(long long) * ((size_t)n_blocks + 1)));
-        PlanGeom pg{ctx->t.px, ctx->t.py, ctx->t.qx, ctx->t.qy, {m.bbmin[0], m.bbmin[1]}, {m.bbmax[0], m.bbmax[1]},
-                    ctx->opt_band_chunks ? ctx->lmax : 0.0};
-        CK(ensure(ctx->b_layout, sizeof(ChunkLayout) * (size_t)n));
-        k_plan_chunks<<<blocks_for(n_blocks * 32, 128), 128, 0, st>>>(n, ctx->t.len, chunk_len, pg, (int *)ctx->b_nch.p,
-                                                                     (ChunkLayout *)ctx->b_layout.p, (int *)ctx->b_blk_chunks.p);
-        CK((exclusive_scan<int, long long>(ctx, (const int *)ctx->b_blk_chunks.p, (long long *)ctx->b_unit_base.p, n_blocks)));
-        CK(cudaMemcpyAsync(&ctx->h_pin[0], (long long *)ctx->b_unit_base.p + n_blocks, sizeof(long long), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        const long long n_units = ctx->h_pin[0];
+        rt_ctx::PlanKey key;
+        key.gen = ctx->trace_gen;
+        key.chunk_len = chunk_len;
+        key.band = ctx->opt_band_chunks;
+        key.order_grid = ctx->opt_order_grid;
+        key.n = n;
+        const bool reuse = ctx->opt_plan_cache && key == ctx->plan_key && ctx->n_units > 0;
+        ChunkPlan &ch = P.ch;
+        if (!reuse) {
+            ctx->plan_key = rt_ctx::PlanKey{};
+            CK(ensure(ctx->b_nch, sizeof(int) * (size_t)n));
+            CK(ensure(ctx->b_blk_chunks, sizeof(int) * (size_t)n_blocks));
+            CK(ensure(ctx->b_unit_base, sizeof(long long) * ((size_t)n_blocks + 1)));
+            PlanGeom pg{ctx->t.px, ctx->t.py, ctx->t.qx, ctx->t.qy, {m.bbmin[0], m.bbmin[1]}, {m.bbmax[0], m.bbmax[1]},
+                        ctx->opt_band_chunks ? ctx->lmax : 0.0};
+            CK(ensure(ctx->b_layout, sizeof(ChunkLayout) * (size_t)n));
+            k_plan_chunks<<<blocks_for(n_blocks * 32, 128), 128, 0, st>>>(n, ctx->t.len, chunk_len, pg, (int *)ctx->b_nch.p,
+                                                                         (ChunkLayout *)ctx->b_layout.p, (int *)ctx->b_blk_chunks.p);
+            CK((exclusive_scan<int, long long>(ctx, (const int *)ctx->b_blk_chunks.p, (long long *)ctx->b_unit_base.p, n_blocks)));
+            CK(cudaMemcpyAsync(&ctx->h_pin[0], (long long *)ctx->b_unit_base.p + n_blocks, sizeof(long long), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            ctx->n_units = ctx->h_pin[0];
+            launches += 5;
+        }
+        const long long n_units = ctx->n_units;
         size_t nc = (size_t)n_units * 32;
         CK(ensure(ctx->b_unit_block, sizeof(int) * (size_t)n_units));
         CK(ensure(ctx->b_ch_i, sizeof(int) * 5 * nc));
         CK(ensure(ctx->b_ch_d, sizeof(double) * 3 * nc));
-        k_fill_units<<<blocks_for(n_blocks, 128), 128, 0, st>>>(n_blocks, (const long long *)ctx->b_unit_base.p,
-                                                                 (int *)ctx->b_unit_block.p);
-        ChunkPlan &ch = P.ch;
+        if (!reuse)
+            k_fill_units<<<blocks_for(n_blocks, 128), 128, 0, st>>>(n_blocks, (const long long *)ctx->b_unit_base.p,
+                                                                     (int *)ctx->b_unit_block.p);
         ch.nch = (int *)ctx->b_nch.p;
         ch.layout = (const ChunkLayout *)ctx->b_layout.p;
         ch.unit_block = (int *)ctx->b_unit_block.p;
@@ -1087,26 +1178,27 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         ch.sum = cd + 2 * nc;
         P.unit_begin = 0;
         P.unit_end = n_units;
-        ctx->n_units = n_units;
-        launches += 5;
         // ---- spatial execution order (counting sort of the units by Morton tile)
         ch.order = nullptr;
         if (ctx->opt_order_grid > 0 && n_units < (1LL << 31)) {
-            int G = std::min(ctx->opt_order_grid, 256);
-            int gp = 1;
-            while (gp < G) gp <<= 1;
-            size_t n_keys = (size_t)gp * gp;
-            CK(ensure(ctx->b_order, sizeof(int) * (size_t)n_units));
-            CK(ensure(ctx->b_okeys, sizeof(int) * (size_t)n_units));
-            CK(ensure(ctx->b_ohist, sizeof(int) * (3 * n_keys + 1)));
-            int *hist = (int *)ctx->b_ohist.p, *ptrs = hist + n_keys, *cursor = ptrs + n_keys + 1;
-            CK(cudaMemsetAsync(hist, 0, sizeof(int) * (3 * n_keys + 1), st));
-            k_unit_keys<<<blocks_for(n_units, 256), 256, 0, st>>>(P, G, (int *)ctx->b_okeys.p, hist);
-            CK((exclusive_scan<int, int>(ctx, hist, ptrs, (long long)n_keys)));
-            k_unit_scatter<<<blocks_for(n_units, 256), 256, 0, st>>>(n_units, (const int *)ctx->b_okeys.p, ptrs, cursor, (int *)ctx->b_order.p);
+            if (!reuse) {
+                int G = std::min(ctx->opt_order_grid, 256);
+                int gp = 1;
+                while (gp < G) gp <<= 1;
+                size_t n_keys = (size_t)gp * gp;
+                CK(ensure(ctx->b_order, sizeof(int) * (size_t)n_units));
+                CK(ensure(ctx->b_okeys, sizeof(int) * (size_t)n_units));
+                CK(ensure(ctx->b_ohist, sizeof(int) * (3 * n_keys + 1)));
+                int *hist = (int *)ctx->b_ohist.p, *ptrs = hist + n_keys, *cursor = ptrs + n_keys + 1;
+                CK(cudaMemsetAsync(hist, 0, sizeof(int) * (3 * n_keys + 1), st));
+                k_unit_keys<<<blocks_for(n_units, 256), 256, 0, st>>>(P, G, (int *)ctx->b_okeys.p, hist);
+                CK((exclusive_scan<int, int>(ctx, hist, ptrs, (long long)n_keys)));
+                k_unit_scatter<<<blocks_for(n_units, 256), 256, 0, st>>>(n_units, (const int *)ctx->b_okeys.p, ptrs, cursor, (int *)ctx->b_order.p);
+                launches += 5;
+            }
             ch.order = (const int *)ctx->b_order.p;
-            launches += 5;
         }
+        if (!reuse) ctx->plan_key = key;
         // ---- seeds, count pass, per-track fix-up
         P.vol = nullptr;
         if (single) {
@@ -1276,6 +1368,17 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
     }
     CK(cudaMemcpyAsync(&ctx->h_pin[4], ctx->b_counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (ctx->deferred_total) {  // optimistic evaluation: the total arrives only now
+        ctx->deferred_total = false;
+        if ((int)ctx->h_pin[10]) {  // cancelled on the device (Segment columns or record pool too small): repeat on the careful path
+            ctx->skip_optimistic_once = true;
+            ctx->redo_careful = true;
+            *verify_failed = true;
+            return RT_OK;
+        }
+        ctx->total_segments = ctx->h_pin[1];
+        ctx->res_nseg = ctx->h_pin[1];
+    }
     if (deferred_verify && (int)ctx->h_pin[2]) {
         *verify_failed = true;
         return RT_OK;
@@ -1345,17 +1448,22 @@ extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rt
     ctx->verify_fallbacks = 0;
     unsigned long long bad = ~0ULL;
     if (mode == 3 && (flags & RT_SEG_LITERAL)) mode = 1;  // (literal-only walks have nothing to gain from per-segment evaluation)
-    for (int attempt = 0; attempt < 3; ++attempt) {
+    for (int attempt = 0; attempt < 4; ++attempt) {
         bool vf = false;
         ctx->fallback_mode = 1;
         int rc = segmentize_once(ctx, tiny_step, k, rtol, max_iter, flags, cb, cb_user, mode, attempt, &vf, &bad);
         if (rc) return rc;
         if (!vf) break;
+        if (ctx->redo_careful) {  // the optimistic evaluation did not fit: same pipeline, sized from the walk's result this time
+            ctx->redo_careful = false;
+            continue;
+        }
         // count and fill disagreed / a geometric fast-path condition failed: redo everything sequentially (the single-walk
         // pipeline asks for the hybrid one when its record pool ran out)
         mode = ctx->fallback_mode;
         ctx->verify_fallbacks += 1;
     }
+    ctx->skip_optimistic_once = false;
     if (n_segments_total) *n_segments_total = ctx->total_segments;
     if (first_bad_uid) *first_bad_uid = 0;
     if (bad_status) *bad_status = 0;
@@ -1839,6 +1947,10 @@ extern "C" int rt_set_option(rt_ctx *ctx, const char *name, double value) {
         ctx->opt_pipeline = (int)value;
     else if (n == "march")
         ctx->opt_march = value != 0.0;
+    else if (n == "plan_cache")
+        ctx->opt_plan_cache = value != 0.0;
+    else if (n == "optimistic")
+        ctx->opt_optimistic = value != 0.0;
     else if (n == "band_chunks")
         ctx->opt_band_chunks = value != 0.0;
     else if (n == "pool_slots" && value >= 0.0)

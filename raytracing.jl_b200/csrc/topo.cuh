@@ -322,6 +322,7 @@ struct EvalParams {
     int *status;   // per track
     double *tsum;  // per track: sum of segment lengths (atomics)
     double rtol;
+    const int *cancel;  // optimistic evaluation cancelled (k_guard): nothing to check
 };
 
 // isapprox(track.l, sum(l.(segments)); rtol)  src/track.jl:171-175.  The atomically accumulated sum differs from the
@@ -330,6 +331,7 @@ struct EvalParams {
 __global__ void k_track_status(const __grid_constant__ EvalParams P) {
     long long t = P.trk_begin + blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= P.trk_end) return;
+    if (P.cancel && *P.cancel) return;
     if (P.status[t] != 0) return;
     const double len = P.t.len[t];
     double sum = P.tsum[t];
