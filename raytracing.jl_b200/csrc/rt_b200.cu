@@ -1396,6 +1396,9 @@ extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rt
                              uint32_t flags, rt_batch_cb cb, void *cb_user, int64_t *n_segments_total, int64_t *first_bad_uid,
                              int32_t *bad_status) {
     if (!ctx) return RT_ERR_ARG;
+    // (whatever goes wrong below, the results of an earlier call are no longer "the last segmentize!": rt_volumes must see that)
+    ctx->segmented = false;
+    ctx->vol_valid = false;
     if (!ctx->traced)
         return fail(ctx, RT_ERR_NOT_TRACED, "Segmentation is intended after tracing. Please, call `trace!` first!");
     if (k < 1 || max_iter < 0) return fail(ctx, RT_ERR_ARG, "rt_segmentize: bad k / max_iter");
