@@ -260,10 +260,11 @@ def strong_block(name, rank, world, local, dist, torch, steps=3):
         ms = tg.timer_stop() / k
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        walk = torch.tensor([float(np.mean([p["count"] for p in ph]))], dtype=torch.float64, device="cuda")
-        ws = [torch.zeros_like(walk) for _ in range(world)]
-        dist.all_gather(ws, walk)
-        return float(t.item()), [float(w.item()) for w in ws]
+        mine = torch.tensor([float(np.mean([p[k] for p in ph])) for k in ("count", "fill", "volumes")] + [ms, tg.info("count_batches")],
+                            dtype=torch.float64, device="cuda")
+        ws = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(ws, mine)
+        return float(t.item()), [[round(float(v), 3) for v in w.tolist()] for w in ws]
 
     out = {"workload": name, "n_cells": int(model.num_cells), "n_azim": n_azim, "delta": delta, "steps": steps}
     one = None
@@ -285,7 +286,8 @@ def strong_block(name, rank, world, local, dist, torch, steps=3):
     dist.all_reduce(n)
     nseg = int(n[0].item())
     out.update({"value": nseg / (ms * 1e-3), "unit": "segments/s", "ms_per_step": ms, "segments_sharded": nseg, "bad_tracks": int(n[1].item()),
-                "walk_ms_per_rank": walks, "walk_spread": (max(walks) - min(walks)) / max(float(np.mean(walks)), 1e-9),
+                "per_rank_ms[walk, evaluation, volumes, step, walk_batches]": walks,
+                "walk_spread": (max(w[0] for w in walks) - min(w[0] for w in walks)) / max(float(np.mean([w[0] for w in walks])), 1e-9),
                 "volumes_sum_over_area": float(tg.volumes.sum() / area)})
     if one is not None:
         out["efficiency_vs_n1"] = one / (world * ms)

@@ -106,6 +106,7 @@ struct rt_ctx {
     // final read-back of the call and repeats the call on the careful path.
     int opt_optimistic = 1;
     bool skip_optimistic_once = false;
+    unsigned long long fit_gen = ~0ULL;  // trace generation whose previous call fitted the Segment columns and the pool in ONE batch
     bool deferred_total = false;
     bool redo_careful = false;         // the repeat asked for by the optimistic path (not a failed verification)
     DevBuf b_guard;
@@ -896,7 +897,8 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
         launches += 6;
         CK(cudaMemcpyAsync(&ctx->h_pin[1], (long long *)ctx->b_offsets.p + e, sizeof(long long), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&ctx->h_pin[9], P.pool_cursor, sizeof(int), cudaMemcpyDeviceToHost, st));
-        if (!multi && !cb && ctx->cap_cfg == 0 && ctx->opt_optimistic && !ctx->skip_optimistic_once && ctx->b_seg_d.p && ctx->cap > 0) {
+        if (!multi && !cb && ctx->cap_cfg == 0 && ctx->opt_optimistic && !ctx->skip_optimistic_once && ctx->fit_gen == ctx->trace_gen &&
+            ctx->b_seg_d.p && ctx->cap > 0) {
             // ---- optimistic evaluation: no host round trip between the walk and the evaluation (see rt_ctx::opt_optimistic)
             CK(ensure(ctx->b_guard, sizeof(int)));
             k_guard<<<1, 1, 0, st>>>((const long long *)ctx->b_offsets.p + e, base, ctx->cap, P.pool_cursor, P.pool_blocks, (int *)ctx->b_guard.p);
@@ -986,6 +988,7 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
         E.tsum = P.tsum;
         E.rtol = rtol;
         const bool split = batch_total > cap;
+        ctx->fit_gen = (!multi && !split) ? ctx->trace_gen : ~0ULL;  // (the next call with these tracks may skip this round trip)
         if (split) {
             if (h_unit_base.empty()) {  // (one walk batch whose segments do not fit after all: the unit ranges are needed now)
                 h_unit_base.resize((size_t)n_blocks + 1);
@@ -1372,6 +1375,7 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         ctx->deferred_total = false;
         if ((int)ctx->h_pin[10]) {  // cancelled on the device (Segment columns or record pool too small): repeat on the careful path
             ctx->skip_optimistic_once = true;
+            ctx->fit_gen = ~0ULL;
             ctx->redo_careful = true;
             *verify_failed = true;
             return RT_OK;
