@@ -330,6 +330,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        from raytracing_jl_b200.distributed import bind_to_gpu_numa
+
+        bind_to_gpu_numa(local)  # pinned result buffers next to this rank's GPU: N downloads do not share one socket's memory
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rt.build()
     model, n_azim, delta = load_workload(args.workload, world, args.strong)
@@ -420,7 +423,10 @@ def main():
             rt.trace_(tg)
             rt.segmentize_(tg, rtol=RTOL, check=False)  # includes the D2H of volumes
             tg.segment_offsets
-            return tg.fetch_segments(pinned=True)  # D2H of every Segment record into pinned host buffers
+            # D2H of every Segment record into pinned host buffers -- over the thin wire: q, len, element (28 B per segment) plus the
+            # list of positions where p is not the preceding q; p is rebuilt on the host when it is first used (the parity block
+            # below does so and compares it with the oracle)
+            return tg.fetch_segments(pinned=True, compact=True)
 
         tg.pin_mesh()  # inputs of the step live in pinned host memory
         for _ in range(2):  # the first call allocates the pinned host buffers of the results
@@ -435,10 +441,32 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         h2d = tg.mesh_h2d_bytes() + 7 * 8 * n_azim // 2
-        d2h = sum(v.nbytes for v in seg.values()) + tg.segment_offsets.nbytes + tg.segment_status.nbytes + tg.volumes.nbytes
-        e2e = {"value": nseg * n_e2e / float(dt.item()), "unit": "segments/s", "h2d_bytes_per_step": int(h2d),
+        d2h = sum(seg[k].nbytes for k in ("qx", "qy", "len", "element")) + 24 * tg.n_exceptions + tg.segment_offsets.nbytes + \
+            tg.segment_status.nbytes + tg.volumes.nbytes
+        # the same step with `len` left on the device too (20 B per segment; rebuilt on the host as norm(p - q), same IEEE operations)
+        def e2e_step20():
+            tg.upload_mesh()
+            rt.trace_(tg)
+            rt.segmentize_(tg, rtol=RTOL, check=False)
+            tg.segment_offsets
+            return tg.fetch_segments(pinned=True, compact="q")
+
+        e2e_step20()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            seg = e2e_step20()
+        torch.cuda.synchronize()
+        dt20 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt20, op=dist.ReduceOp.MAX)
+        wire20 = {"value": nseg * n_e2e / float(dt20.item()), "ms_per_step": 1e3 * float(dt20.item()) / n_e2e,
+                  "d2h_bytes_per_step": int(d2h - 8 * nseg_local), "what": "as e2e, with q + element only on the wire (len = norm(p - q) rebuilt on the host)"}
+        e2e = {"value": nseg * n_e2e / float(dt.item()), "unit": "segments/s", "h2d_bytes_per_step": int(h2d), "wire20": wire20,
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(dt.item()) / n_e2e,
-               "what": "rt_mesh_upload + rt_trace + rt_segmentize + rt_volumes + rt_segment_offsets + rt_segments_download"}
+               "wire_bytes_per_segment": 28, "p_exceptions": int(tg.n_exceptions),
+               "what": "rt_mesh_upload + rt_trace + rt_segmentize + rt_volumes + rt_segment_offsets + rt_segments_download_compact "
+                       "(q, len, element + exception list; p[i] = q[i-1] rebuilt lazily on the host, bit-identical to the full download)"}
 
     # ---- parity in the same run: the GPU's records of sampled uid blocks against the CPU oracle, bit for bit; at N = 1 the sample
     # is the one the cpu_baseline is timed on, at N > 1 every rank checks a few small blocks of its own shard

@@ -147,6 +147,15 @@ int rt_segment_offsets(rt_ctx *ctx, int64_t *offsets /* n_shard+1 */, int32_t *s
  * it fitted), SoA, in uid order then walk order. Any pointer may be NULL. */
 int rt_segments_download(rt_ctx *ctx, double *px, double *py, double *qx, double *qy, double *len,
                          int32_t *element);
+/* The same records over a thinner wire: 28 instead of 44 bytes per segment cross the bus.  Inside a track, `p` of a segment is
+ * `q` of the one before it (src/track.jl:165: the walk continues from q), so only q, len and element are copied; the positions
+ * where p differs in any bit from the preceding q -- the first segment of every track, the neighbourhood of the few segments the
+ * literal walk produced -- come as an unordered exception list (index into the resident batch, px, py).  The caller rebuilds
+ * p[i] = q[i-1] and patches the listed positions: the result is bit-identical to rt_segments_download (tests/test_gpu_parity.py).
+ * *n_exceptions receives the number of exceptions found; if it exceeds max_exceptions the call returns RT_ERR_NOMEM after the
+ * columns have been copied, and can be repeated with larger buffers.  Column pointers may be NULL. */
+int rt_segments_download_compact(rt_ctx *ctx, double *qx, double *qy, double *len, int32_t *element, int64_t max_exceptions,
+                                 int64_t *exc_index, double *exc_px, double *exc_py, int64_t *n_exceptions);
 /* device-resident view of the resident batch for on-GPU consumers (transport sweeps) */
 int rt_segments_device(rt_ctx *ctx, rt_batch *view);
 

@@ -89,6 +89,7 @@ SYMBOLS = {
                                 C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "rt_segment_offsets": (C.c_int, [_vp, _vp, _vp]),
     "rt_segments_download": (C.c_int, [_vp] + [_vp] * 6),
+    "rt_segments_download_compact": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, C.POINTER(C.c_int64)]),
     "rt_segments_device": (C.c_int, [_vp, C.POINTER(rt_batch)]),
     "rt_volumes": (C.c_int, [_vp, _vp]),
     "rt_tracks_device": (C.c_int, [_vp, C.POINTER(rt_track_view)]),

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+from collections.abc import Mapping
 from dataclasses import dataclass
 from enum import IntEnum
 
@@ -111,11 +112,74 @@ class Segment:  # src/segment.jl:23-29
         return f"Segment(p={self.p}, q={self.q}, ell={self.ell}, element={self.element})"
 
 
+class SegmentColumns(Mapping):
+    """The SoA columns px, py, qx, qy, len, element of the resident Segment batch.  After a COMPACT download
+    (``fetch_segments(compact=True)``, rt_segments_download_compact) only qx, qy, len, element crossed the bus; ``px`` / ``py``
+    are rebuilt on first use from p[i] = q[i-1] plus the exception list -- whole columns through ``cols["px"]``, or just the
+    range of one track through ``p_range`` (what ``track.segments`` uses).  Both are bit-identical to a full download."""
+
+    KEYS = ("px", "py", "qx", "qy", "len", "element")
+
+    def __init__(self, cols, exceptions=None):
+        self._cols = dict(cols)
+        self._exc = None
+        if exceptions is not None:
+            idx, ex, ey = exceptions
+            o = np.argsort(idx, kind="stable")
+            self._exc = (idx[o], ex[o], ey[o])
+
+    @property
+    def compact(self):
+        return self._exc is not None
+
+    def __getitem__(self, key):
+        if key not in self._cols:
+            if key == "len" and self._exc is not None:
+                # Segment(p, q): norm(p - q) (src/segment.jl:32) with the operations of the device code, in the same order:
+                # IEEE subtract, multiply, add and square root, none of them fused -- the same bits
+                dx, dy = self["px"] - self._cols["qx"], self["py"] - self._cols["qy"]
+                self._cols["len"] = np.sqrt(dx * dx + dy * dy)
+            elif key in ("px", "py") and self._exc is not None:
+                idx, ex, ey = self._exc
+                for name, q, e in (("px", self._cols["qx"], ex), ("py", self._cols["qy"], ey)):
+                    p = np.empty_like(q)
+                    p[1:] = q[:-1]
+                    p[idx] = e
+                    self._cols[name] = p
+            else:
+                raise KeyError(key)
+        return self._cols[key]
+
+    def __iter__(self):
+        return iter(self.KEYS)
+
+    def __len__(self):
+        return len(self.KEYS)
+
+    def p_range(self, lo, hi):
+        """(px, py) of the segments [lo, hi) of the resident batch without rebuilding the whole columns"""
+        if "px" in self._cols:
+            return self._cols["px"][lo:hi], self._cols["py"][lo:hi]
+        idx, ex, ey = self._exc
+        out = []
+        a, b = np.searchsorted(idx, lo), np.searchsorted(idx, hi)
+        for q, e in ((self._cols["qx"], ex), (self._cols["qy"], ey)):
+            p = np.empty(hi - lo, q.dtype)
+            if hi - lo > 1:
+                p[1:] = q[lo:hi - 1]
+            if lo > 0 and hi > lo:
+                p[0] = q[lo - 1]
+            p[idx[a:b] - lo] = e[a:b]
+            out.append(p)
+        return out[0], out[1]
+
+
 class SegmentList:
     """``track.segments``: a read-only sequence of Segment records backed by the SoA buffers."""
 
     def __init__(self, tg, lo, hi):
         self._tg, self._lo, self._hi = tg, lo, hi
+        self._p = None
 
     def __len__(self):
         return self._hi - self._lo
@@ -129,7 +193,9 @@ class SegmentList:
         if not 0 <= i < n:
             raise IndexError(i)
         s, o = self._tg.segments, self._lo + i
-        return Segment(np.array([s["px"][o], s["py"][o]]), np.array([s["qx"][o], s["qy"][o]]), float(s["len"][o]),
+        if self._p is None:
+            self._p = s.p_range(self._lo, self._hi)
+        return Segment(np.array([self._p[0][i], self._p[1][i]]), np.array([s["qx"][o], s["qy"][o]]), float(s["len"][o]),
                        int(s["element"][o]))
 
     def __iter__(self):
@@ -137,7 +203,9 @@ class SegmentList:
 
     def arrays(self):
         """SoA slices (px, py, qx, qy, len, element) of this track."""
-        return {k: v[self._lo:self._hi] for k, v in self._tg.segments.items()}
+        s = self._tg.segments
+        px, py = s.p_range(self._lo, self._hi)
+        return {"px": px, "py": py, **{k: s[k][self._lo:self._hi] for k in ("qx", "qy", "len", "element")}}
 
 
 class Track:  # src/track.jl:42-57 ; a view over the track SoA
@@ -296,7 +364,9 @@ class TrackGenerator(TrackLayout):
         self.bcs = bcs if bcs is not None else BoundaryConditions()
         self.tiny_step = float(tiny_step)
         self.volume_correction = bool(volume_correction)
-        self.volumes = np.zeros(mesh.num_cells)
+        self._pinned_volumes = _lib.PinnedArray((max(mesh.num_cells, 1),), np.float64)  # (rt_volumes copies straight into it)
+        self.volumes = self._pinned_volumes.array[:mesh.num_cells]
+        self.volumes[:] = 0.0
         self.tracks = _TracksByAngle(self)
         self.tracks_by_uid = _TracksByUid(self)
         self.shard = (int(shard[0]), int(shard[1]))
@@ -415,30 +485,54 @@ class TrackGenerator(TrackLayout):
             self._resident = (int(view.uid_begin), int(view.uid_end), int(view.offset_base), int(view.n_segments))
         return self._resident
 
-    def fetch_segments(self, pinned: bool = False):
+    def fetch_segments(self, pinned: bool = False, compact: bool = False, max_exceptions: int | None = None):
         """Device -> host copy of the Segment records of the resident batch.  By default into fresh numpy arrays the caller owns.
         ``pinned=True`` stages into page-locked buffers that are REUSED by the next pinned fetch of this TrackGenerator (full PCIe
         rate, no allocation per call): the arrays returned by an earlier pinned fetch then show the new data.  A buffer that has
-        to grow is never freed under a view that is still alive (its memory is released when the last view dies)."""
+        to grow is never freed under a view that is still alive (its memory is released when the last view dies).
+        ``compact=True`` moves 28 instead of 44 bytes per segment (rt_segments_download_compact): q, len, element plus the list of
+        positions where p is not the preceding q; ``px`` / ``py`` are rebuilt on the host on first use (SegmentColumns).
+        ``compact="q"`` leaves ``len`` on the device as well (20 bytes per segment): it is rebuilt as norm(p - q) with the same
+        IEEE operations (not after ``correct_volumes``, which rescales the resident lengths)."""
         if not self._segmented:
             raise RuntimeError("call segmentize_ first")
         L = _lib.lib()
         n = self.resident_batch()[3]
         names = [("px", np.float64), ("py", np.float64), ("qx", np.float64), ("qy", np.float64), ("len", np.float64),
                  ("element", np.int32)]
-        out = {}
-        for name, dt in names:
-            if pinned:
-                buf = self._pinned.get(name)
-                if buf is None or buf.array.shape[0] < n:
-                    buf = _lib.PinnedArray((max(n, 1),), dt)  # (the old buffer lives on for as long as views of it do)
-                    self._pinned[name] = buf
-                out[name] = buf.array[:n]
-            else:
-                out[name] = np.zeros(n, dt)
-        _lib.check(self._ctx, L.rt_segments_download(self._ctx, *[_lib.ptr(out[k]) for k, _ in names]))
-        self._segments = out
-        return out
+        if compact:
+            names = names[2:]
+            if compact == "q":
+                names = [nd for nd in names if nd[0] != "len"]
+
+        def buffer(name, dt, count):
+            if not pinned:
+                return np.zeros(count, dt)
+            buf = self._pinned.get(name)
+            if buf is None or buf.array.shape[0] < count:
+                buf = _lib.PinnedArray((max(count, 1),), dt)  # (the old buffer lives on for as long as views of it do)
+                self._pinned[name] = buf
+            return buf.array[:count]
+
+        out = {name: buffer(name, dt, n) for name, dt in names}
+        if not compact:
+            _lib.check(self._ctx, L.rt_segments_download(self._ctx, *[_lib.ptr(out[k]) for k, _ in names]))
+            self._segments = SegmentColumns(out)
+            return self._segments
+        cap = max(getattr(self, "_exc_cap", 0), 4 * (self.uid_end - self.uid_begin) + n // 64 + 1024) if max_exceptions is None else int(max_exceptions)
+        for _ in range(2):
+            ei, ex, ey = buffer("exc_index", np.int64, cap), buffer("exc_px", np.float64, cap), buffer("exc_py", np.float64, cap)
+            k = C.c_int64(0)
+            rc = L.rt_segments_download_compact(self._ctx, *[_lib.ptr(out.get(kk)) for kk in ("qx", "qy", "len", "element")], cap,
+                                                _lib.ptr(ei), _lib.ptr(ex), _lib.ptr(ey), C.byref(k))
+            if rc != -10:  # RT_ERR_NOMEM: more exceptions than room -- once more with the count the call reported
+                break
+            cap = int(k.value) + 1024
+        _lib.check(self._ctx, rc)
+        self._exc_cap = cap if max_exceptions is None else getattr(self, "_exc_cap", 0)
+        self.n_exceptions = int(k.value)
+        self._segments = SegmentColumns(out, (ei[:k.value], ex[:k.value], ey[:k.value]))
+        return self._segments
 
     # ---- sweep-facing device views (SURVEY 8f-1) ----------------------------------------------------
     def track_view(self):

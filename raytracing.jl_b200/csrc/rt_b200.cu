@@ -81,6 +81,9 @@ struct rt_ctx {
     DevBuf b_order, b_okeys, b_ohist;  // spatial execution order of the units
     DevBuf b_omega, b_sigma, b_tau;  // sweep-facing exports (sweep.cuh)
     DevBuf b_area, b_factor;         // exact element volumes, volume-correction factors (sweep.cuh)
+    DevBuf b_exc;                    // compact download: exception list (sweep.cuh k_p_exceptions)
+    cudaStream_t aux_stream = nullptr;  // ... built on a side stream while the columns cross the bus
+    cudaEvent_t ev_aux = nullptr;
     bool area_valid = false;
     long long *h_pin = nullptr;  // page-locked scratch for the small device->host read-backs of rt_segmentize (16 words)
     DevBuf b_scratch, b_gcounts, b_gcursor;  // rt_mesh_upload staging (kept between uploads)
@@ -253,7 +256,7 @@ extern "C" void rt_destroy(rt_ctx *ctx) {
                      &ctx->b_scratch, &ctx->b_gcounts,   &ctx->b_gcursor,
                      &ctx->b_omega,   &ctx->b_sigma,     &ctx->b_tau,
                      &ctx->b_pool,    &ctx->b_pool_next, &ctx->b_pool_cursor,
-                     &ctx->b_area,    &ctx->b_factor,    &ctx->b_layout,    &ctx->b_vol_alt,  &ctx->b_guard};
+                     &ctx->b_area,    &ctx->b_factor,    &ctx->b_layout,    &ctx->b_vol_alt,  &ctx->b_guard,  &ctx->b_exc};
     for (DevBuf *b : all) release(*b);
     for (int ph = 0; ph < 6; ++ph)
         for (int q = 0; q < 2; ++q)
@@ -264,6 +267,8 @@ extern "C" void rt_destroy(rt_ctx *ctx) {
     }
     for (cudaEvent_t e : {ctx->ev_fill_done, ctx->ev_vol_free[0], ctx->ev_vol_free[1]})
         if (e) cudaEventDestroy(e);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->ev_aux) cudaEventDestroy(ctx->ev_aux);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     delete ctx;
@@ -1512,6 +1517,53 @@ extern "C" int rt_segments_download(rt_ctx *ctx, double *px, double *py, double 
     if (len) CK(cudaMemcpyAsync(len, ctx->s_len, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     if (element) CK(cudaMemcpyAsync(element, ctx->s_elem, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return RT_OK;
+}
+
+extern "C" int rt_segments_download_compact(rt_ctx *ctx, double *qx, double *qy, double *len, int32_t *element, int64_t max_exceptions,
+                                            int64_t *exc_index, double *exc_px, double *exc_py, int64_t *n_exceptions) {
+    if (!ctx || !ctx->segmented) return fail(ctx, RT_ERR_ARG, "rt_segments_download_compact: call rt_segmentize first");
+    if (max_exceptions < 0 || !n_exceptions || (max_exceptions > 0 && (!exc_index || !exc_px || !exc_py)))
+        return fail(ctx, RT_ERR_ARG, "rt_segments_download_compact: bad exception buffers");
+    CK(cudaSetDevice(ctx->device));
+    const long long n = ctx->res_nseg;
+    *n_exceptions = 0;
+    if (n == 0) return RT_OK;
+    cudaStream_t st = ctx->stream;
+    // the exception list is built on a side stream (a 0.3 ms kernel over the resident columns) while the four columns that do
+    // cross the bus are already on their way
+    if (!ctx->aux_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming));
+    }
+    cudaStream_t ax = ctx->aux_stream;
+    const size_t cap = (size_t)max_exceptions;
+    CK(ensure(ctx->b_exc, 16 + cap * 24));
+    unsigned long long *d_cnt = (unsigned long long *)ctx->b_exc.p;
+    long long *d_idx = (long long *)((char *)ctx->b_exc.p + 16);
+    double *d_px = (double *)(d_idx + cap), *d_py = d_px + cap;
+    CK(cudaEventRecord(ctx->ev_aux, st));  // (the evaluation that wrote the columns)
+    CK(cudaStreamWaitEvent(ax, ctx->ev_aux, 0));
+    CK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), ax));
+    k_p_exceptions<<<blocks_for(n, 256), 256, 0, ax>>>(n, ctx->s_px, ctx->s_py, ctx->s_qx, ctx->s_qy, (long long)cap, d_cnt, d_idx, d_px, d_py);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&ctx->h_pin[11], d_cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ax));
+    if (qx) CK(cudaMemcpyAsync(qx, ctx->s_qx, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (qy) CK(cudaMemcpyAsync(qy, ctx->s_qy, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (len) CK(cudaMemcpyAsync(len, ctx->s_len, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (element) CK(cudaMemcpyAsync(element, ctx->s_elem, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(ax));
+    const long long k = ctx->h_pin[11];
+    *n_exceptions = k;
+    if (k > 0 && k <= (long long)cap) {
+        CK(cudaMemcpyAsync(exc_index, d_idx, sizeof(long long) * (size_t)k, cudaMemcpyDeviceToHost, ax));
+        CK(cudaMemcpyAsync(exc_px, d_px, sizeof(double) * (size_t)k, cudaMemcpyDeviceToHost, ax));
+        CK(cudaMemcpyAsync(exc_py, d_py, sizeof(double) * (size_t)k, cudaMemcpyDeviceToHost, ax));
+        CK(cudaStreamSynchronize(ax));
+    }
+    CK(cudaStreamSynchronize(st));
+    if (k > (long long)cap)
+        return fail(ctx, RT_ERR_NOMEM, "rt_segments_download_compact: %lld exceptions, room for %lld (call again with larger buffers)", k, (long long)cap);
     return RT_OK;
 }
 

@@ -70,4 +70,28 @@ __global__ void k_scale_lengths(long long n_seg, const int *__restrict__ element
     len[s] = len[s] * factor[element[s] - 1];
 }
 
+// ---- compact download of the Segment records (rt_segments_download_compact) ------------------------------------------------
+// Inside a track the entry point of a segment IS the exit point of the one before it (the walk re-locates from q, and on generic
+// transitions the two are the same bits, eval3.cuh), so `p` does not have to cross PCIe: the host rebuilds p[i] = q[i-1] and
+// patches the few positions where that does not hold -- the first segment of every track and the neighbourhood of literal
+// records.  This kernel lists those positions: (index, px, py) of every resident segment whose p differs, in any bit, from the q of
+// its predecessor in the columns.  One thread per segment; the list is unordered (the host sorts the ~0.2 % it receives).
+__global__ void k_p_exceptions(long long n_seg, const double *__restrict__ px, const double *__restrict__ py, const double *__restrict__ qx,
+                               const double *__restrict__ qy, long long cap, unsigned long long *__restrict__ count, long long *__restrict__ idx,
+                               double *__restrict__ epx, double *__restrict__ epy) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_seg) return;
+    const double x = px[i], y = py[i];
+    bool differs = i == 0;
+    if (!differs) differs = __double_as_longlong(x) != __double_as_longlong(qx[i - 1]) || __double_as_longlong(y) != __double_as_longlong(qy[i - 1]);
+    if (differs) {
+        const unsigned long long k = atomicAdd(count, 1ULL);
+        if ((long long)k < cap) {
+            idx[k] = i;
+            epx[k] = x;
+            epy[k] = y;
+        }
+    }
+}
+
 }  // namespace rt

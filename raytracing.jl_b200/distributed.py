@@ -53,6 +53,30 @@ def plan_shards(tg, n_parts: int) -> np.ndarray:
     return np.maximum.accumulate(bounds)
 
 
+def bind_to_gpu_numa(device_index: int) -> bool:
+    """Restrict this process to the CPUs NVML reports as local to the GPU (its NUMA node), so that the page-locked host buffers
+    it allocates afterwards -- the destination of the Segment downloads -- are placed next to that GPU's PCIe root.  With one
+    process per GPU this keeps N concurrent device->host streams from funnelling into one socket's memory.  Returns False (and
+    changes nothing) when NVML or the affinity call is unavailable."""
+    try:
+        import pynvml as nv
+
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [int(v) for v in vis.split(",") if v.strip().isdigit()]
+        phys = ids[device_index] if ids and device_index < len(ids) else device_index
+        h = nv.nvmlDeviceGetHandleByIndex(phys)
+        n_cpu = os.cpu_count() or 1
+        words = nv.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, mask in enumerate(words) for b in range(64) if (mask >> b) & 1 and 64 * w + b < n_cpu}
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False
+
+
 def env_rank():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 

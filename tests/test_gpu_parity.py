@@ -561,6 +561,46 @@ def test_cfg5_named_size_sampled_against_oracle():
     tg.close()
 
 
+def test_compact_download_is_bit_identical(pincell_model):
+    """rt_segments_download_compact: q, len, element + the exception list rebuild exactly the columns of the full download --
+    on a mesh with many literal records (pincell: every track starts and ends on a boundary node for delta = 0.08), with tiny
+    chunks, with a batched evaluation (only the last batch is resident), and track by track (p_range)."""
+    from raytracing_jl_b200 import _lib as L
+
+    cases = [(pincell_model, 16, 0.08, None, 0), (pincell_model, 32, 0.01, 5, 0), (rt.synth.jittered_triangle_mesh(60, 60, seed=3), 16, 0.01, None, 0),
+             (pincell_model, 32, 0.01, None, 20000)]
+    for model, n_azim, delta, chunk, cap in cases:
+        tg = rt.TrackGenerator(model, n_azim, delta, bcs=bcs_of((1, 0, 2, 2)))
+        rt.trace_(tg)
+        if chunk:
+            tg.set_option("chunk_segments", chunk)
+            tg.set_option("target_walkers", 1e9)
+        if cap:
+            L.check(tg._ctx, L.lib().rt_set_segment_capacity(tg._ctx, cap))
+        rt.segmentize_(tg, check=False)
+        full = {k: v.copy() for k, v in tg.fetch_segments().items()}
+        for pinned in (False, True):
+            comp = tg.fetch_segments(pinned=pinned, compact=True)
+            assert comp.compact and 0 < tg.n_exceptions < max(64, 0.2 * full["px"].size)
+            u0, u1, base, n = tg.resident_batch()
+            off = tg.segment_offsets - base
+            for uid in (u0, (u0 + u1) // 2, u1 - 1):  # track by track, before the whole columns are rebuilt
+                lo, hi = int(off[uid - tg.uid_begin]), int(off[uid - tg.uid_begin + 1])
+                px, py = comp.p_range(lo, hi)
+                assert np.array_equal(px, full["px"][lo:hi]) and np.array_equal(py, full["py"][lo:hi])
+                segs = tg.tracks_by_uid[uid].segments
+                if len(segs):
+                    assert np.array_equal(segs[0].p, [full["px"][lo], full["py"][lo]]) and np.array_equal(segs[-1].p, [full["px"][hi - 1], full["py"][hi - 1]])
+            for k in api.SegmentColumns.KEYS:
+                assert np.array_equal(comp[k], full[k]), k
+        small = tg.fetch_segments(compact=True, max_exceptions=8)  # too small a list: the call reports the count and is repeated
+        assert all(np.array_equal(small[k], full[k]) for k in api.SegmentColumns.KEYS)
+        small = tg.fetch_segments(compact="q")  # 20 bytes per segment: len rebuilt as norm(p - q) too
+        assert "len" not in small._cols
+        assert all(np.array_equal(small[k], full[k]) for k in api.SegmentColumns.KEYS)
+        tg.close()
+
+
 def test_resident_batch_guards_and_k_limit(pincell_model):
     """Track.segments refuses tracks whose batch is not resident (instead of indexing another batch's columns); k beyond
     RT_MAX_K is rejected instead of being clamped; k within it reaches the kNN fallback unchanged."""
