@@ -247,7 +247,8 @@ int rt_selftest_division(rt_ctx *ctx, int64_t n_threads, uint64_t seed, int32_t 
  * disagreement; 3 restarts in mode 0 when its record
  * pool runs out), "march" (0: k_topo<2> instead of k_march in pipeline 3), "band_chunks" (0: uniform chunks also where a track
  * runs along the bounding box), "pool_slots" / "pool_extra" (test hooks: chunk slots per count batch, spare record blocks),
- * "debug_verify_fail" (test hook) */
+ * "debug_verify_fail", "debug_clear_pool" (test hooks), "plan_cache" (0: rebuild the chunk plan in every call), "optimistic" (0: always read
+ * the segment total back before the evaluation is launched) */
 int rt_set_option(rt_ctx *ctx, const char *name, double value);
 /* CUDA-event stopwatch on the context's launching stream (bench harness: torch.cuda.Event cannot see it). */
 int rt_timer_start(rt_ctx *ctx);

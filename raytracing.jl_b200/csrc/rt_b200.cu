@@ -102,6 +102,8 @@ struct rt_ctx {
         bool operator==(const PlanKey &o) const { return gen == o.gen && chunk_len == o.chunk_len && band == o.band && order_grid == o.order_grid && n == o.n; }
     } plan_key;
     bool plan_has_order = false;
+    int opt_debug_clear_pool = 0;      // test hook (initcheck): zero the record pool before every walk, so that the evaluation's speculative
+                                       // load of a chunk's first records (issued before its count is known) never reads unwritten words
     int opt_plan_cache = 1;            // 0: rebuild the chunk plan in every call (test knob)
     // Optimistic evaluation: when the previous call's Segment columns are still allocated, the evaluation is launched right behind
     // the walk WITHOUT reading the segment total back first; a one-thread guard kernel compares the total (and the record pool's
@@ -887,6 +889,7 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
         ctx->h_pin[8] = 0;
         *(int *)&ctx->h_pin[8] = (int)slots;
         CK(cudaMemcpyAsync(P.pool_cursor, &ctx->h_pin[8], sizeof(int), cudaMemcpyHostToDevice, st));
+        if (ctx->opt_debug_clear_pool) CK(cudaMemsetAsync(ctx->b_pool.p, 0, ctx->b_pool.bytes, st));
         if (B0 > 0) tic(ctx, 2);  // (the first batch's count phase started with the chunk plan)
         k_seed<<<blocks_for(slots, 128), 128, 0, st>>>(P);
         if (ctx->opt_march)
@@ -2006,6 +2009,8 @@ extern "C" int rt_set_option(rt_ctx *ctx, const char *name, double value) {
         ctx->opt_pipeline = (int)value;
     else if (n == "march")
         ctx->opt_march = value != 0.0;
+    else if (n == "debug_clear_pool")
+        ctx->opt_debug_clear_pool = value != 0.0;
     else if (n == "plan_cache")
         ctx->opt_plan_cache = value != 0.0;
     else if (n == "optimistic")

@@ -254,7 +254,10 @@ __global__ void __launch_bounds__(128) k_seed(const __grid_constant__ WalkParams
     if (t >= P.n_tracks) return;
     int n = P.ch.nch[t];
     if (j >= n) return;
-    P.ch.seed_cell[cidx] = -1;
+    P.ch.seed_cell[cidx] = -1;  // (every field is written: the evaluation requests the seed point of a chunk before it knows whether it needs it)
+    P.ch.seed_kexit[cidx] = 0;
+    P.ch.seed_qx[cidx] = 0.0;
+    P.ch.seed_qy[cidx] = 0.0;
     if (j == 0) return;
     int az = P.t.azim[t];
     Line trk{P.t.a[t], P.t.b[t], P.t.c[t]};
