@@ -61,6 +61,7 @@ def lib():
         L.orc_nn_brute.restype = C.c_int32
         L.orc_knn.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_int32, _i32p]
         L.orc_point_in_triangle.argtypes = [vp, C.c_int32, C.c_double, C.c_double]
+        L.orc_point_in_element.argtypes = [vp, C.c_int32, C.c_double, C.c_double]
         L.orc_find_element.argtypes = [vp, C.c_double, C.c_double, C.c_int]
         L.orc_find_element.restype = C.c_int32
         L.orc_inboundary.argtypes = [vp, C.c_double, C.c_double, C.c_double]
@@ -132,6 +133,9 @@ class OracleMesh:
 
     def point_in_triangle(self, cell, x, y):
         return bool(lib().orc_point_in_triangle(self._h, cell, x, y))
+
+    def point_in_element(self, cell, x, y):
+        return bool(lib().orc_point_in_element(self._h, cell, x, y))
 
     def inboundary(self, x, y, atol):
         return bool(lib().orc_inboundary(self._h, x, y, atol))

@@ -53,6 +53,8 @@ int32_t orc_nn(const orc_mesh *m, double x, double y);                       /* 
 int orc_knn(const orc_mesh *m, double x, double y, int k, int32_t skip, int32_t *ids); /* sorted */
 int32_t orc_nn_brute(const orc_mesh *m, double x, double y);
 int orc_point_in_triangle(const orc_mesh *m, int32_t cell, double x, double y);
+/* triangles: the test above; 4-node cells: point_in_quadrangle (src/mesh.jl:184-201) */
+int orc_point_in_element(const orc_mesh *m, int32_t cell, double x, double y);
 int32_t orc_find_element(const orc_mesh *m, double x, double y, int k);      /* 1-based cell or -1 */
 int orc_inboundary(const orc_mesh *m, double x, double y, double atol);
 /* returns 0 ok / ORC_ERR_UNDEF; pq = px,py,qx,qy; edges = local edge (0..2) that produced p and q or -1 */

@@ -1,6 +1,6 @@
 """B200-native drop-in for the trace! -> segmentize! hot path of RayTracing.jl."""
 from .mesh import DiscreteModelFromFile, GmshDiscreteModel, Mesh, UnstructuredDiscreteModel  # noqa: F401
-from . import synth  # noqa: F401
+from . import plotdata, synth  # noqa: F401
 from .api import (  # noqa: F401
     AzimuthalQuadrature, Backward, BoundaryConditions, BoundaryType, DirectionType, DomainError, Forward, Periodic,
     Reflective, Segment, SegmentColumns, Track, TrackGenerator, TrackLayout, Vacuum, bc_bwd, bc_fwd, dir_next_track_bwd, dir_next_track_fwd, ell,

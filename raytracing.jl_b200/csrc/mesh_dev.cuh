@@ -38,7 +38,9 @@ struct DevMesh {
     const int *twin;     // [3*cell + k]: encoded entry half-edge of the neighbour across edge k (as tw1/tw2)
     int n_nodes, n_cells;
     const double2 *xy;      // node coordinates
-    const int *cell_nodes;  // 3*n_cells, 0-based, stored (Gridap) order
+    const int *cell_nodes;  // 3*n_cells, 0-based, stored (Gridap) order; mixed meshes: the CSR data of cell_ptrs
+    const int *cell_ptrs;   // nullptr: every cell is a triangle.  Otherwise 0-based CSR offsets (n_cells + 1) of a MIXED mesh of
+                            // 3- and 4-node cells: only the literal walk runs on it, from xy / cell_nodes directly
     const int *nc_ptrs;     // node -> cells CSR, 0-based, caller's order (src/mesh.jl:27)
     const int *nc_data;
     const CellRec *cells;
@@ -158,6 +160,27 @@ struct MeshScalars {
 __device__ __forceinline__ void atomic_max_double(double *addr, double v) {
     // values are non-negative: ordering of the bit patterns equals ordering of the doubles
     atomicMax((unsigned long long *)addr, (unsigned long long)__double_as_longlong(v));
+}
+
+// mixed meshes (3- and 4-node cells): the density scalars only -- edges are consecutive stored nodes, like in intersections()
+// (src/intersection.jl:46-51); the area of a quadrilateral is the shoelace sum over its stored cycle
+__global__ void k_mesh_scalars_generic(int n_cells, const int *cell_ptrs, const int *cell_nodes, const double2 *xy, MeshScalars *sc) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    const int b = cell_ptrs[c], nn = cell_ptrs[c + 1] - b;
+    double lmax = 0.0, smax = 0.0, esum = 0.0, a2 = 0.0;
+    for (int i = 0; i < nn; ++i) {
+        const double2 p = xy[cell_nodes[b + i]], q = xy[cell_nodes[b + (i + 1 == nn ? 0 : i + 1)]];
+        const double l = norm2(p.x - q.x, p.y - q.y);
+        lmax = fmax(lmax, l);
+        esum += l;
+        smax = fmax(smax, fmax(fabs(p.x), fabs(p.y)));
+        a2 += p.x * q.y - q.x * p.y;
+    }
+    atomic_max_double(&sc->lmax, lmax);
+    atomic_max_double(&sc->smax, smax);
+    atomicAdd(&sc->edge_sum, esum);
+    atomicAdd(&sc->area, 0.5 * fabs(a2));
 }
 
 // per cell: vertex coordinates, neighbours, edge records, geometric quality numbers
@@ -424,28 +447,55 @@ __device__ __forceinline__ bool point_in_triangle(const DevMesh &m, int cell, do
     return (lo <= l1 && l1 <= hi) && (lo <= l2 && l2 <= hi) && (lo <= l3 && l3 <= hi);
 }
 
+// the same test on three explicit nodes (mixed meshes: no CellRec table)
+__device__ __forceinline__ bool point_in_triangle_nodes(const DevMesh &m, int n1, int n2, int n3, double x, double y) {
+    const double2 a = m.xy[n1], b = m.xy[n2], c = m.xy[n3];
+    const double x1 = a.x, y1 = a.y, x2 = b.x, y2 = b.y, x3 = c.x, y3 = c.y;
+    double d = x1 * (y2 - y3) + y1 * (x3 - x2) + (x2 * y3 - y2 * x3);
+    double l1 = ((y2 - y3) * x + (x3 - x2) * y + (x2 * y3 - x3 * y2)) / d;
+    double l2 = ((y3 - y1) * x + (x1 - x3) * y + (x3 * y1 - x1 * y3)) / d;
+    double l3 = ((y1 - y2) * x + (x2 - x1) * y + (x1 * y2 - x2 * y1)) / d;
+    const double lo = 0.0 - kRtol, hi = 1.0 + kRtol;
+    return (lo <= l1 && l1 <= hi) && (lo <= l2 && l2 <= hi) && (lo <= l3 && l3 <= hi);
+}
+
+// point_in_element (src/mesh.jl:148-150) dispatched on the number of nodes: triangles as above; 4-node cells by
+// point_in_quadrangle (src/mesh.jl:184-201): the four triangles (k, k+1, k+2) of the stored cycle
+__device__ __noinline__ bool point_in_cell_generic(const DevMesh &m, int cell, double x, double y) {
+    const int b = m.cell_ptrs[cell], nn = m.cell_ptrs[cell + 1] - b;
+    const int *nid = m.cell_nodes + b;
+    if (nn == 3) return point_in_triangle_nodes(m, nid[0], nid[1], nid[2], x, y);
+    for (int i = 0; i < 4; ++i)
+        if (point_in_triangle_nodes(m, nid[i], nid[(i + 1) & 3], nid[(i + 2) & 3], x, y)) return true;
+    return false;
+}
+
+// MIXED is a compile-time switch: only the kernels that walk mixed meshes (k_walk<*, true>) contain the generic cell code, the
+// triangle kernels are compiled exactly as before
+template <bool MIXED = false>
 __device__ __forceinline__ int scan_node_cells(const DevMesh &m, int node, double x, double y) {
     for (int q = m.nc_ptrs[node]; q < m.nc_ptrs[node + 1]; ++q) {
         int cell = m.nc_data[q];
-        if (point_in_triangle(m, cell, x, y)) return cell;
+        if (MIXED ? point_in_cell_generic(m, cell, x, y) : point_in_triangle(m, cell, x, y)) return cell;
     }
     return -1;
 }
 
 // find_element(mesh, x, k)  src/mesh.jl:103-146 ; returns 0-based cell or -1
+template <bool MIXED = false>
 __device__ RT_SLOWPATH_INLINE int find_element(const DevMesh &m, double x, double y, int k, unsigned long long *nq) {
     KBest s;
     s.k = 1;
     knn_query(m, x, y, -1, s);
     if (nq) nq[0]++;
     int nn = s.id[0];
-    int c = scan_node_cells(m, nn, x, y);
+    int c = scan_node_cells<MIXED>(m, nn, x, y);
     if (c >= 0) return c;
     s.k = min(k, kMaxK);  // (k <= kMaxK is checked by rt_segmentize)
     knn_query(m, x, y, nn, s);
     if (nq) nq[1]++;
     for (int i = 0; i < s.n; ++i) {
-        c = scan_node_cells(m, s.id[i], x, y);
+        c = scan_node_cells<MIXED>(m, s.id[i], x, y);
         if (c >= 0) return c;
     }
     return -1;
@@ -460,8 +510,77 @@ __device__ __forceinline__ bool inboundary(const DevMesh &m, double x, double y,
 
 // intersections(mesh, cell, track)  src/intersection.jl:34-119 (triangles: 3 edges, at most 3 hits).
 // Returns 0, or 4 (RT_TRACK_UNDEF) when the 3-hit selection never assigns x_int1. e_p/e_q: local edges of p and q.
+// mixed meshes: the reference's loop over the edges (i, i+1) of the stored node cycle of a 3- or 4-node cell, general_form of
+// every edge evaluated on the spot like the reference does, at most four hits (src/intersection.jl:42-44), the farthest pair when
+// there are three or four (:81-95).  Returns 0, or 4 (RT_TRACK_UNDEF) when that selection never assigns x_int1.
+__device__ __noinline__ int intersections_generic(const DevMesh &m, int cell, const Line &trk, bool phi_lt_half_pi, P2 &p, P2 &q, int &e_p,
+                                                  int &e_q) {
+    const int b = m.cell_ptrs[cell], nn = m.cell_ptrs[cell + 1] - b;
+    P2 ip[4];
+    int ie[4];
+    int n_int = 0;
+    bool parallel_found = false;
+    for (int i = 0; i < nn; ++i) {
+        const int j = (i == nn - 1) ? 0 : i + 1;
+        const double2 a = m.xy[m.cell_nodes[b + i]], c = m.xy[m.cell_nodes[b + j]];
+        const P2 p1{a.x, a.y}, p2{c.x, c.y};
+        const Line L = general_form(p1, p2);
+        P2 X;
+        if (intersection(trk, L, X)) {
+            parallel_found = true;
+            continue;
+        }
+        if (!point_in_segment(p1, p2, norm2(p1.x - p2.x, p1.y - p2.y), X)) continue;
+        if (n_int < 4) {
+            ip[n_int] = X;
+            ie[n_int] = i;
+        }
+        n_int++;
+    }
+    e_p = e_q = -1;
+    if (n_int == 3 || n_int == 4) {
+        double l = 0.0;
+        int s1 = -1, s2 = -1;
+        for (int i = 2; i <= n_int; ++i)  // for i in 2:n_int, j in i:n_int: x1 = pts[i-1], x2 = pts[j]
+            for (int j = i; j <= n_int; ++j) {
+                const double li = norm2(ip[i - 2].x - ip[j - 1].x, ip[i - 2].y - ip[j - 1].y);
+                if (li > l) {
+                    s1 = i - 2;
+                    s2 = j - 1;
+                    l = li;
+                }
+            }
+        if (s1 < 0) return 4;
+        const bool first = order_first(phi_lt_half_pi, ip[s1], ip[s2]);
+        p = first ? ip[s1] : ip[s2];
+        q = first ? ip[s2] : ip[s1];
+        e_p = first ? ie[s1] : ie[s2];
+        e_q = first ? ie[s2] : ie[s1];
+        return 0;
+    }
+    if (n_int == 2) {
+        if (!parallel_found && isapprox_pt(ip[0], ip[1])) {
+            p = ip[0];
+            q = ip[1];
+            e_p = ie[0];
+            e_q = ie[1];
+            return 0;
+        }
+        const bool first = order_first(phi_lt_half_pi, ip[0], ip[1]);
+        p = first ? ip[0] : ip[1];
+        q = first ? ip[1] : ip[0];
+        e_p = first ? ie[0] : ie[1];
+        e_q = first ? ie[1] : ie[0];
+        return 0;
+    }
+    p.x = p.y = q.x = q.y = 0.0;
+    return 0;
+}
+
+template <bool MIXED = false>
 __device__ RT_SLOWPATH_INLINE int intersections(const DevMesh &m, int cell, const Line &trk, bool phi_lt_half_pi, P2 &p, P2 &q,
                                           int &e_p, int &e_q) {
+    if (MIXED) return intersections_generic(m, cell, trk, phi_lt_half_pi, p, q, e_p, e_q);
     const CellRec &r = m.cells[cell];
     P2 ip[3];
     int ie[3];

@@ -53,7 +53,9 @@ struct rt_ctx {
 
     // mesh
     bool has_mesh = false;
+    bool mixed = false;  // 3- and 4-node cells: literal walk only
     DevMesh m{};
+    DevBuf b_cell_ptrs;
     DevBuf b_xy, b_cell_nodes, b_nc_ptrs, b_nc_data, b_nbr, b_cells, b_edges, b_qual, b_bdist, b_sc, b_grid_ptrs,
         b_grid_nodes, b_twin, b_he, b_node_reach;
     double clear_tiny = -1.0;
@@ -104,6 +106,7 @@ struct rt_ctx {
     bool plan_has_order = false;
     int opt_debug_clear_pool = 0;      // test hook (initcheck): zero the record pool before every walk, so that the evaluation's speculative
                                        // load of a chunk's first records (issued before its count is known) never reads unwritten words
+    double opt_band_cost = 28.0;       // shard planning: cost of one boundary-band cell in fast transitions (measured: cfg4 on 8 GPUs)
     int opt_plan_cache = 1;            // 0: rebuild the chunk plan in every call (test knob)
     // Optimistic evaluation: when the previous call's Segment columns are still allocated, the evaluation is launched right behind
     // the walk WITHOUT reading the segment total back first; a one-thread guard kernel compares the total (and the record pool's
@@ -247,7 +250,7 @@ extern "C" void rt_destroy(rt_ctx *ctx) {
     if (ctx->coll_stream) cudaStreamSynchronize(ctx->coll_stream);  // a collective may still be in flight
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
-    DevBuf *all[] = {&ctx->b_xy,      &ctx->b_cell_nodes, &ctx->b_nc_ptrs,  &ctx->b_nc_data, &ctx->b_nbr,     &ctx->b_cells,
+    DevBuf *all[] = {&ctx->b_cell_ptrs, &ctx->b_xy,      &ctx->b_cell_nodes, &ctx->b_nc_ptrs,  &ctx->b_nc_data, &ctx->b_nbr,     &ctx->b_cells,
                      &ctx->b_edges,   &ctx->b_qual,       &ctx->b_bdist,    &ctx->b_sc,      &ctx->b_grid_ptrs, &ctx->b_grid_nodes,
                      &ctx->b_ang_d,   &ctx->b_ang_i,      &ctx->b_trk_d,    &ctx->b_trk_i,   &ctx->b_trk_l,   &ctx->b_trk_c,
                      &ctx->b_err,     &ctx->b_count,      &ctx->b_status,   &ctx->b_offsets, &ctx->b_tile,    &ctx->b_vol,
@@ -310,15 +313,22 @@ extern "C" int rt_mesh_upload(rt_ctx *ctx, int32_t n_nodes, const double *xy, in
         return fail(ctx, RT_ERR_ARG, "rt_mesh_upload: null or empty mesh arrays");
     const bool dev_nc = node_cell_ptrs == nullptr;  // build the vertex -> cells table on the device
     const bool dev_bb = bb_min == nullptr;          // reduce the bounding box on the device
-    for (int32_t c = 0; c < n_cells; ++c)
-        if (cell_ptrs[c + 1] - cell_ptrs[c] != 3)
-            return fail(ctx, RT_ERR_ARG, "rt_mesh_upload: cell %d is not a triangle (reference src/mesh.jl:149-150)", c + 1);
+    bool mixed = false;
+    for (int32_t c = 0; c < n_cells; ++c) {
+        const int nn = cell_ptrs[c + 1] - cell_ptrs[c];
+        if (nn == 4)
+            mixed = true;
+        else if (nn != 3)
+            return fail(ctx, RT_ERR_ARG, "rt_mesh_upload: cell %d has %d nodes (triangles and quadrilaterals only)", c + 1, nn);
+    }
+    if (mixed && dev_nc) return fail(ctx, RT_ERR_ARG, "rt_mesh_upload: a mesh with quadrilaterals needs the vertex -> cells table from the caller");
+    const size_t n_cd = (size_t)(cell_ptrs[n_cells] - 1);  // entries of the cell -> nodes table
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     tic(ctx, 0);
     size_t n_nc = dev_nc ? (size_t)3 * n_cells : (size_t)(node_cell_ptrs[n_nodes] - 1);
     CK(ensure(ctx->b_xy, sizeof(double2) * (size_t)n_nodes));
-    CK(ensure(ctx->b_cell_nodes, sizeof(int) * 3 * (size_t)n_cells));
+    CK(ensure(ctx->b_cell_nodes, sizeof(int) * n_cd));
     CK(ensure(ctx->b_nc_ptrs, sizeof(int) * ((size_t)n_nodes + 1)));
     CK(ensure(ctx->b_nc_data, sizeof(int) * n_nc));
     CK(ensure(ctx->b_nbr, sizeof(int) * 3 * (size_t)n_cells));
@@ -329,7 +339,7 @@ extern "C" int rt_mesh_upload(rt_ctx *ctx, int32_t n_nodes, const double *xy, in
     CK(ensure(ctx->b_sc, sizeof(MeshScalars)));
     // stage the 1-based tables through a (persistent) scratch buffer and convert on the device; no host synchronisation here:
     // the three tables use disjoint scratch regions
-    const size_t tab_n[3] = {(size_t)3 * n_cells, dev_nc ? 0 : (size_t)n_nodes + 1, dev_nc ? 0 : n_nc};
+    const size_t tab_n[3] = {n_cd, dev_nc ? 0 : (size_t)n_nodes + 1, dev_nc ? 0 : n_nc};
     CK(ensure(ctx->b_scratch, sizeof(int32_t) * (tab_n[0] + tab_n[1] + tab_n[2])));
     CK(cudaMemcpyAsync(ctx->b_xy.p, xy, sizeof(double) * 2 * (size_t)n_nodes, cudaMemcpyHostToDevice, st));
     const int32_t *tab_src[3] = {cell_data, node_cell_ptrs, node_cell_data};
@@ -343,6 +353,15 @@ extern "C" int rt_mesh_upload(rt_ctx *ctx, int32_t n_nodes, const double *xy, in
         tab_off += tab_n[q];
     }
 
+    if (mixed) {  // the CSR offsets of the cell -> nodes table (triangle meshes do not need them: 3 * cell)
+        DevBuf stage;
+        CK(ensure(stage, sizeof(int32_t) * ((size_t)n_cells + 1)));
+        CK(ensure(ctx->b_cell_ptrs, sizeof(int) * ((size_t)n_cells + 1)));
+        CK(cudaMemcpyAsync(stage.p, cell_ptrs, sizeof(int32_t) * ((size_t)n_cells + 1), cudaMemcpyHostToDevice, st));
+        k_to_zero_based<<<blocks_for((long long)n_cells + 1, 256), 256, 0, st>>>((const int32_t *)stage.p, (int *)ctx->b_cell_ptrs.p, (long long)n_cells + 1);
+        CK(cudaStreamSynchronize(st));
+        release(stage);
+    }
     if (dev_nc) {  // count -> scan -> fill -> sort (ascending cell id around every node, src/mesh.jl:27)
         DevBuf deg, cur;
         CK(ensure(deg, sizeof(int) * (size_t)n_nodes));
@@ -377,6 +396,7 @@ extern "C" int rt_mesh_upload(rt_ctx *ctx, int32_t n_nodes, const double *xy, in
     m.n_cells = n_cells;
     m.xy = (const double2 *)ctx->b_xy.p;
     m.cell_nodes = (const int *)ctx->b_cell_nodes.p;
+    m.cell_ptrs = mixed ? (const int *)ctx->b_cell_ptrs.p : nullptr;
     m.nc_ptrs = (const int *)ctx->b_nc_ptrs.p;
     m.nc_data = (const int *)ctx->b_nc_data.p;
     m.cells = (const CellRec *)ctx->b_cells.p;
@@ -401,8 +421,17 @@ extern "C" int rt_mesh_upload(rt_ctx *ctx, int32_t n_nodes, const double *xy, in
     m.grid_ptrs = (const int *)ctx->b_grid_ptrs.p;
     m.grid_nodes = (const int *)ctx->b_grid_nodes.p;
 
-    k_neighbours<<<blocks_for(3LL * n_cells, 256), 256, 0, st>>>(n_cells, m.cell_nodes, m.nc_ptrs, m.nc_data, (int *)ctx->b_nbr.p);
     CK(cudaMemsetAsync(ctx->b_sc.p, 0, sizeof(MeshScalars), st));
+    if (mixed) {
+        // only the literal walk runs on a mixed mesh: no neighbour table, no cell / edge / half-edge records -- just the density
+        // scalars that size the buffers
+        k_mesh_scalars_generic<<<blocks_for(n_cells, 128), 128, 0, st>>>(n_cells, m.cell_ptrs, m.cell_nodes, m.xy, (MeshScalars *)ctx->b_sc.p);
+        m.cells = nullptr;
+        m.edges = nullptr;
+        m.twin = nullptr;
+        m.he = nullptr;
+    } else {
+    k_neighbours<<<blocks_for(3LL * n_cells, 256), 256, 0, st>>>(n_cells, m.cell_nodes, m.nc_ptrs, m.nc_data, (int *)ctx->b_nbr.p);
     k_cell_records<<<blocks_for(n_cells, 128), 128, 0, st>>>(m, (const int *)ctx->b_nbr.p, (CellRec *)ctx->b_cells.p,
                                                              (EdgeRec *)ctx->b_edges.p, (float *)ctx->b_qual.p,
                                                              (float *)ctx->b_bdist.p, (MeshScalars *)ctx->b_sc.p);
@@ -416,6 +445,7 @@ extern "C" int rt_mesh_upload(rt_ctx *ctx, int32_t n_nodes, const double *xy, in
     CK(cudaMemsetAsync(ctx->b_node_reach.p, 0, sizeof(float) * (size_t)n_nodes, st));
     k_node_reach<<<blocks_for(n_cells, 128), 128, 0, st>>>(m, (const CellRec *)ctx->b_cells.p, (const MeshScalars *)ctx->b_sc.p,
                                                            (float *)ctx->b_node_reach.p);
+    }
     // grid: count -> scan -> fill
     DevBuf &counts = ctx->b_gcounts, &cursor = ctx->b_gcursor;
     CK(ensure(counts, sizeof(int) * n_bins));
@@ -436,6 +466,7 @@ extern "C" int rt_mesh_upload(rt_ctx *ctx, int32_t n_nodes, const double *xy, in
     ctx->area = sc.area;
     ctx->clear_tiny = -1.0;
     ctx->trace_gen++;
+    ctx->mixed = mixed;
     ctx->has_mesh = true;
     ctx->area_valid = false;
     ctx->traced = false;
@@ -470,6 +501,7 @@ extern "C" int rt_mesh_node_cells(rt_ctx *ctx, int32_t *node_cell_ptrs, int32_t 
 
 extern "C" int rt_mesh_neighbours(rt_ctx *ctx, int32_t *cell_nbr) {
     if (!ctx || !ctx->has_mesh || !cell_nbr) return fail(ctx, RT_ERR_ARG, "rt_mesh_neighbours: no mesh");
+    if (ctx->mixed) return fail(ctx, RT_ERR_ARG, "rt_mesh_neighbours: triangle meshes only");
     CK(cudaSetDevice(ctx->device));
     size_t n = 3 * (size_t)ctx->m.n_cells;
     CK(cudaMemcpy(cell_nbr, ctx->b_nbr.p, sizeof(int) * n, cudaMemcpyDeviceToHost));
@@ -527,6 +559,7 @@ static void fill_trace_params(rt_ctx *ctx, TraceParams &P, const int32_t bcs[4])
         P.bbmax[q] = ctx->m.bbmax[q];
     }
     P.len_only = nullptr;
+    P.cost_w = 0.0;
     P.err = (unsigned long long *)ctx->b_err.p;
 }
 
@@ -712,6 +745,7 @@ extern "C" int rt_plan_shards(rt_ctx *ctx, int32_t n_azim_2, const int64_t *n_tr
     P.n = n;
     P.t = TrackSoA{};
     P.len_only = (double *)lens.p;
+    P.cost_w = ctx->edge_sum > 0.0 ? ctx->opt_band_cost * (kPi * ctx->area / ctx->edge_sum) : 0.0;  // band_cost segments, as a length
     k_trace<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(P);
     CK((exclusive_scan<double, double>(ctx, (const double *)lens.p, (double *)cum.p, n)));
     k_split_points<<<blocks_for(n_parts + 1, 64), 64, 0, ctx->stream>>>((const double *)cum.p, n, n_parts, (long long *)db.p);
@@ -1220,7 +1254,10 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
             k_topo<0><<<blocks_for(n_units * 32, kTopoThreads), kTopoThreads, 0, st>>>(P);
         } else {
             P.vol = (want_vol && count_only) ? ctx->vol_acc : nullptr;
-            k_walk<false><<<blocks_for(n_units * 32, kWalkThreads), kWalkThreads, 0, st>>>(P);
+            if (ctx->mixed)
+                k_walk<false, true><<<blocks_for(n_units * 32, kWalkThreads), kWalkThreads, 0, st>>>(P);
+            else
+                k_walk<false><<<blocks_for(n_units * 32, kWalkThreads), kWalkThreads, 0, st>>>(P);
         }
         k_fixup_tracks<<<blocks_for(n, 128), 128, 0, st>>>(P);
         launches += 3;
@@ -1333,7 +1370,10 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
             }
             const long long nseg_b = (total > cap ? h_off[e] : total) - P.offset_base;
             {
-                k_walk<true><<<blocks_for((P.unit_end - P.unit_begin) * 32, kWalkThreads), kWalkThreads, 0, st>>>(P);
+                if (ctx->mixed)
+                    k_walk<true, true><<<blocks_for((P.unit_end - P.unit_begin) * 32, kWalkThreads), kWalkThreads, 0, st>>>(P);
+                else
+                    k_walk<true><<<blocks_for((P.unit_end - P.unit_begin) * 32, kWalkThreads), kWalkThreads, 0, st>>>(P);
                 launches += 1;
                 if (topo_count) {
                     E.trk_begin = b;
@@ -1426,7 +1466,8 @@ extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rt
     ctx->segmented = false;
     ctx->vol_valid = false;
 
-    if (ctx->clear_tiny != tiny_step) {
+    if (ctx->mixed) flags |= RT_SEG_LITERAL | RT_SEG_NO_CHUNKS | RT_SEG_SEQUENTIAL;  // quadrilaterals: the reference's walk, step by step
+    if (!ctx->mixed && ctx->clear_tiny != tiny_step) {
         k_finalize_clear<<<blocks_for(m.n_cells, 128), 128, 0, st>>>(m, (CellRec *)ctx->b_cells.p, (HalfEdge *)ctx->b_he.p,
                                                                      (const float *)ctx->b_qual.p, (const float *)ctx->b_bdist.p,
                                                                      (const MeshScalars *)ctx->b_sc.p,
@@ -1668,6 +1709,7 @@ extern "C" int rt_optical_lengths(rt_ctx *ctx, int32_t n_groups, const double *s
 // exact element volumes and the volume correction
 // ------------------------------------------------------------------------------------------------------
 static int ensure_areas(rt_ctx *ctx) {
+    if (ctx->mixed) return fail(ctx, RT_ERR_ARG, "element_volume is defined for triangles (src/trackgenerator.jl:402-411): triangle meshes only");
     if (ctx->area_valid) return RT_OK;
     const int nc = ctx->m.n_cells;
     CK(ensure(ctx->b_area, sizeof(double) * (size_t)nc));
@@ -1901,6 +1943,10 @@ extern "C" int rt_info(rt_ctx *ctx, const char *key, double *value) {
         *value = (double)ctx->n_units;
     else if (k == "segment_capacity")
         *value = (double)ctx->cap;
+    else if (k == "rho")  // expected cell crossings per unit track length (Cauchy-Crofton): sum of edge lengths / (pi * area)
+        *value = ctx->area > 0.0 ? ctx->edge_sum / (kPi * ctx->area) : 0.0;
+    else if (k == "band_cost")
+        *value = ctx->opt_band_cost;
     else if (k == "count_batches")
         *value = (double)ctx->count_batches;
     else
@@ -2011,6 +2057,8 @@ extern "C" int rt_set_option(rt_ctx *ctx, const char *name, double value) {
         ctx->opt_march = value != 0.0;
     else if (n == "debug_clear_pool")
         ctx->opt_debug_clear_pool = value != 0.0;
+    else if (n == "band_cost" && value >= 0.0)
+        ctx->opt_band_cost = value;
     else if (n == "plan_cache")
         ctx->opt_plan_cache = value != 0.0;
     else if (n == "optimistic")

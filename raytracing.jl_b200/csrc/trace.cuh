@@ -15,7 +15,9 @@ struct TraceParams {
     long long uid_begin;  // 1-based uid of the first track of the shard
     long long n;          // tracks in the shard
     TrackSoA t;
-    double *len_only;             // if non-null: only write the track length here (shard planning)
+    double *len_only;             // if non-null: only write the track's COST here (shard planning): its length plus cost_w times
+                                  // the reciprocal sines of the angles at which it leaves and reaches the bounding box
+    double cost_w;
     unsigned long long *err;      // min over failing tracks of (uid << 4 | code)
 };
 
@@ -85,7 +87,13 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
     qy += P.bbmin[1];
     double len = norm2(px - qx, py - qy);
     if (P.len_only) {
-        P.len_only[idx] = len;
+        // Shard planning.  A track costs its segments (~ its length) plus what the boundary band costs at both ends: within one
+        // cell of the bounding box every transition is examined exactly on the slow side of the walk, and a track that meets the
+        // boundary at an angle theta stays in that band for ~1/sin(theta) cells ("chunk layout and the boundary band").
+        const double t = fabs(mm), c = 1.0 / sqrt(1.0 + t * t), sn = t * c;  // |cos phi|, sin phi
+        const double s_in = (j <= nx) ? sn : c;            // starts on the bottom side / on a lateral side
+        const double s_out = (qy == Dy + P.bbmin[1]) ? sn : c;  // ends on the top side / on a lateral side
+        P.len_only[idx] = len + P.cost_w * (1.0 / fmax(s_in, 1e-6) + 1.0 / fmax(s_out, 1e-6));
         return;
     }
     Line abc = general_form(P2{px, py}, P2{qx, qy});

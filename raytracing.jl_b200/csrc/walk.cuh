@@ -350,6 +350,7 @@ struct LitOut {
     unsigned long long nq[2];  // nearest-node / knn queries
 };
 
+template <bool MIXED = false>
 __device__ RT_LITERAL_CALL void literal_until_push(const WalkParams &P, const LitIn &in, LitOut &out) {
     const DevMesh &m = P.m;
     Line trk{in.a, in.b, in.c};
@@ -375,9 +376,9 @@ __device__ RT_LITERAL_CALL void literal_until_push(const WalkParams &P, const Li
             out.code = END_TRACK;
             return;
         }
-        int e = find_element(m, xpx, xpy, 2, out.nq);
+        int e = find_element<MIXED>(m, xpx, xpy, 2, out.nq);
         if (e < 0) {
-            e = find_element(m, xpx, xpy, P.k, out.nq);
+            e = find_element<MIXED>(m, xpx, xpy, P.k, out.nq);
             if (e < 0) {
                 out.status = 1;  // "Try increasing `k`", src/track.jl:141
                 return;
@@ -390,7 +391,7 @@ __device__ RT_LITERAL_CALL void literal_until_push(const WalkParams &P, const Li
         }
         P2 p, q;
         int e_p, e_q;
-        int rc = intersections(m, e, trk, in.right, p, q, e_p, e_q);
+        int rc = intersections<MIXED>(m, e, trk, in.right, p, q, e_p, e_q);
         if (rc) {
             out.status = rc;
             return;
@@ -413,7 +414,7 @@ __device__ RT_LITERAL_CALL void literal_until_push(const WalkParams &P, const Li
 }
 
 // ---- the walk ----------------------------------------------------------------------------------------------
-template <bool FILL>
+template <bool FILL, bool MIXED = false>
 __global__ void __launch_bounds__(kWalkThreads, RT_WALK_MIN_BLOCKS) k_walk(const __grid_constant__ WalkParams P) {
     const unsigned FULL = 0xffffffffu;
     const DevMesh &m = P.m;
@@ -665,7 +666,7 @@ __global__ void __launch_bounds__(kWalkThreads, RT_WALK_MIN_BLOCKS) k_walk(const
             // advance_step: x + step*Point2D(cos phi, sin phi), src/point.jl:43
             LitIn in{ta, tb, tc, P.tiny * P.ang.cosp[az], P.tiny * P.ang.sinp[az], qx, qy, cur, right, j == 0 && nseg == 0};
             LitOut o;
-            literal_until_push(P, in, o);
+            literal_until_push<MIXED>(P, in, o);
             if (P.counters) {
                 atomicAdd(&P.counters[1], (unsigned long long)o.iters);
                 atomicAdd(&P.counters[2], o.nq[0]);

@@ -12,9 +12,11 @@ import numpy as np
 from . import _lib
 
 
-def track_lengths(tg) -> np.ndarray:
-    """Lengths of all tracks in uid order (vectorised restatement of src/trackgenerator.jl:188-226; only used to
-    balance shards, not for results). Needs tg.azimuthal_quadrature.phis, i.e. the tables of trace_."""
+def track_costs(tg, cost_w: float = 0.0) -> np.ndarray:
+    """Planning cost of all tracks in uid order: the length (vectorised restatement of src/trackgenerator.jl:188-226; only used to
+    balance shards, not for results) plus ``cost_w`` times the reciprocal sines of the angles at which the track leaves and
+    reaches the bounding box -- the cells it spends in the boundary band, where every transition takes the slow side of the
+    walk.  Needs tg.azimuthal_quadrature.phis, i.e. the tables of trace_.  (Twin of k_trace's planning branch, trace.cuh.)"""
     from .api import nazim2, nazim4
 
     aq = tg.azimuthal_quadrature
@@ -39,13 +41,30 @@ def track_lengths(tg) -> np.ndarray:
         else:
             qy = np.where(bad, py - m * px, qy)
             qx = np.where(bad, 0.0, qx)
-        out.append(np.hypot(px - qx, py - qy))
+        cost = np.hypot(px - qx, py - qy)
+        if cost_w > 0.0:
+            t = abs(m)
+            c = 1.0 / np.sqrt(1.0 + t * t)
+            sn = t * c
+            s_in = np.where(onx, sn, c)
+            s_out = np.where(bad, c, sn)
+            cost = cost + cost_w * (1.0 / np.maximum(s_in, 1e-6) + 1.0 / np.maximum(s_out, 1e-6))
+        out.append(cost)
     return np.concatenate(out)
 
 
+def track_lengths(tg) -> np.ndarray:
+    return track_costs(tg, 0.0)
+
+
 def plan_shards(tg, n_parts: int) -> np.ndarray:
-    """bounds[r] .. bounds[r+1] (1-based uids, end exclusive) with equal total track length per part."""
-    lens = track_lengths(tg)
+    """bounds[r] .. bounds[r+1] (1-based uids, end exclusive) with equal total planning cost per part (track_costs; the weight of
+    the boundary band comes from the context when the TrackGenerator has one: band_cost fast transitions per band cell)."""
+    cost_w = 0.0
+    if getattr(tg, "_ctx", None):
+        rho = tg.info("rho")
+        cost_w = tg.info("band_cost") / rho if rho > 0 else 0.0
+    lens = track_costs(tg, cost_w)
     cum = np.concatenate([[0.0], np.cumsum(lens)])
     targets = cum[-1] * (np.arange(1, n_parts) / n_parts)
     inner = np.searchsorted(cum, targets, side="left") + 1

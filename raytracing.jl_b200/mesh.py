@@ -16,11 +16,13 @@ import numpy as np
 
 @dataclass
 class UnstructuredDiscreteModel:
-    """Triangle mesh in Gridap's layout. ``cell_ptrs``/``cell_data`` are 1-based (Gridap ``Table``)."""
+    """Mesh in Gridap's layout: ``cell_ptrs``/``cell_data`` are the 1-based CSR ``Table`` of cell -> nodes.  Triangles (what the
+    reference walks, src/mesh.jl:149-150) and, as SURVEY 8(f)-4 asks, 4-node quadrilaterals whose stored nodes form a CYCLE
+    (consecutive nodes are edges: the assumption of ``intersections``, src/intersection.jl:46-51)."""
 
     node_coordinates: np.ndarray  # (n_nodes, 2) float64, contiguous x,y pairs
     cell_ptrs: np.ndarray  # (n_cells + 1,) int32, 1-based
-    cell_data: np.ndarray  # (3 * n_cells,) int32, 1-based node ids
+    cell_data: np.ndarray  # int32, 1-based node ids, 3 or 4 per cell
     labels: dict = field(default_factory=dict)
 
     def __post_init__(self):
@@ -47,8 +49,26 @@ class UnstructuredDiscreteModel:
         ptrs = (np.arange(n + 1, dtype=np.int64) * 3 + 1).astype(np.int32)
         return cls(np.asarray(xy, dtype=np.float64), ptrs, (tri.reshape(-1) + 1).astype(np.int32), **kw)
 
+    @classmethod
+    def from_cells(cls, xy: np.ndarray, cells0, **kw):
+        """Build from a list of 0-based node tuples of length 3 or 4, node order kept as given (quadrilaterals: a cycle)."""
+        counts = np.fromiter((len(c) for c in cells0), dtype=np.int64, count=len(cells0))
+        ptrs = np.concatenate([[1], 1 + np.cumsum(counts)]).astype(np.int32)
+        data = (np.fromiter((n for c in cells0 for n in c), dtype=np.int64, count=int(counts.sum())) + 1).astype(np.int32)
+        return cls(np.asarray(xy, dtype=np.float64), ptrs, data, **kw)
+
+    @property
+    def cell_sizes(self) -> np.ndarray:
+        return np.diff(self.cell_ptrs.astype(np.int64))
+
+    @property
+    def has_quads(self) -> bool:
+        return bool(np.any(self.cell_sizes == 4))
+
     def triangles0(self) -> np.ndarray:
         """0-based (n_cells, 3) view of the cell table (triangles only)."""
+        if self.has_quads:
+            raise ValueError("triangles0: the mesh holds quadrilaterals")
         return self.cell_data.reshape(-1, 3).astype(np.int64) - 1
 
 
@@ -61,8 +81,8 @@ def DiscreteModelFromFile(path: str) -> UnstructuredDiscreteModel:
     xy = np.asarray(g["node_coordinates"], dtype=np.float64).reshape(-1, int(g.get("Dp", 2)))[:, :2]
     ptrs = np.asarray(g["cell_node_ids"]["ptrs"], dtype=np.int32)
     data = np.asarray(g["cell_node_ids"]["data"], dtype=np.int32)
-    if not np.all(np.diff(ptrs) == 3):
-        raise ValueError("only linear triangles are supported (reference src/mesh.jl:149-150)")
+    if not np.all(np.isin(np.diff(ptrs), (3, 4))):
+        raise ValueError("only linear triangles and quadrilaterals are supported")
     lab = d.get("labeling", {})
     labels = {"names": lab.get("names"), "tags": lab.get("tags"), "entities_2": lab.get("entities_2")}
     return UnstructuredDiscreteModel(xy, ptrs, data, labels)

@@ -43,6 +43,37 @@ def jittered_triangle_mesh(nx: int, ny: int, lx: float = 1.0, ly: float = 1.0, j
     return UnstructuredDiscreteModel.from_triangles(xy, tri)
 
 
+def mixed_quad_triangle_mesh(nx: int, ny: int, lx: float = 1.0, ly: float = 1.0, jitter: float = 0.2, seed: int = 1234,
+                             quad_fraction: float = 0.5, x0: float = 0.0, y0: float = 0.0) -> UnstructuredDiscreteModel:
+    """nx x ny jittered quadrilaterals of which a seeded fraction stays a 4-node cell (nodes stored counter-clockwise, i.e. as
+    a cycle) while the others are split into two triangles: the mixed mesh of SURVEY 8(f)-4."""
+    rng = np.random.default_rng(seed)
+    hx, hy = lx / nx, ly / ny
+    ix, iy = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), indexing="xy")
+    x = x0 + ix * hx
+    y = y0 + iy * hy
+    x[:, -1] = x0 + lx
+    y[-1, :] = y0 + ly
+    interior = np.zeros_like(x, dtype=bool)
+    interior[1:-1, 1:-1] = True
+    x = np.where(interior, x + rng.uniform(-jitter * hx, jitter * hx, size=x.shape), x)
+    y = np.where(interior, y + rng.uniform(-jitter * hy, jitter * hy, size=y.shape), y)
+    xy = np.stack([x.reshape(-1), y.reshape(-1)], axis=1)
+    nid = (iy * (nx + 1) + ix).astype(np.int64)
+    keep = rng.uniform(size=(ny, nx)) < quad_fraction
+    cells = []
+    for j in range(ny):
+        for i in range(nx):
+            a, b, c, d = int(nid[j, i]), int(nid[j, i + 1]), int(nid[j + 1, i + 1]), int(nid[j + 1, i])  # counter-clockwise
+            if keep[j, i]:
+                cells.append((a, b, c, d))
+            elif (i + j) % 2:
+                cells += [tuple(sorted((a, b, c))), tuple(sorted((a, c, d)))]
+            else:
+                cells += [tuple(sorted((a, b, d))), tuple(sorted((b, c, d)))]
+    return UnstructuredDiscreteModel.from_cells(xy, cells)
+
+
 def pin_cell_template(pitch: float, r_inner: float, clad: float, h: float, seed: int = 1234):
     """One pin cell [0,pitch]^2: rings of nodes inside r_inner + clad (two rings sit exactly on the pin
     and cladding radii), a jittered lattice in the moderator, uniformly spaced border nodes so that
@@ -117,6 +148,13 @@ def pin_lattice_mesh(n_pins: int, pitch: float = 1.26, r_inner: float = 0.4096, 
 
 def mesh_area(model: UnstructuredDiscreteModel) -> float:
     xy = model.node_coordinates
+    if model.has_quads:  # shoelace sum over every cell's stored node cycle
+        ptrs, data = model.cell_ptrs.astype(np.int64) - 1, model.cell_data.astype(np.int64) - 1
+        nxt = np.arange(data.size) + 1
+        last = ptrs[1:] - 1
+        nxt[last] = ptrs[:-1]
+        cross = xy[data, 0] * xy[data[nxt], 1] - xy[data[nxt], 0] * xy[data, 1]
+        return float(np.abs(np.add.reduceat(cross, ptrs[:-1])).sum() / 2.0)
     t = model.triangles0()
     p0, p1, p2 = xy[t[:, 0]], xy[t[:, 1]], xy[t[:, 2]]
     a2 = (p1[:, 0] - p0[:, 0]) * (p2[:, 1] - p0[:, 1]) - (p2[:, 0] - p0[:, 0]) * (p1[:, 1] - p0[:, 1])

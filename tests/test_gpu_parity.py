@@ -601,6 +601,35 @@ def test_compact_download_is_bit_identical(pincell_model):
         tg.close()
 
 
+@pytest.mark.parametrize("frac,n_azim,delta,bcs", [(0.5, 16, 0.02, (1, 1, 1, 1)), (1.0, 8, 0.03, (0, 2, 0, 2)), (0.15, 32, 0.011, (2, 2, 1, 1))])
+def test_mixed_quad_triangle_mesh_matches_oracle(frac, n_azim, delta, bcs):
+    """meshes that mix triangles and 4-node quadrilaterals (all quadrilaterals for frac = 1).  Cells are located
+    with the reference's point_in_quadrangle (src/mesh.jl:184-201), chords come from its 4-edge intersections()
+    (src/intersection.jl:42-44, 81-95): only the literal walk runs on such a mesh, and it reproduces the oracle bit for bit."""
+    model = rt.synth.mixed_quad_triangle_mesh(31, 23, 1.5, 1.1, jitter=0.22, seed=17, quad_fraction=frac, x0=-0.3, y0=0.7)
+    assert model.has_quads
+    otg, tg = run_both(model, n_azim, delta, bcs=bcs)
+    assert_tracks_equal(otg, tg)
+    assert_segments_equal(otg, tg)
+    assert_volumes_close(otg, tg)
+    assert otg.bad_status == 0 and tg.stats()["fast_transitions"] == 0  # every step re-located like src/track.jl:122
+    quad_ids = np.nonzero(model.cell_sizes == 4)[0] + 1
+    assert np.isin(tg.segments["element"], quad_ids).mean() > 0.3 * frac  # (a quadrilateral is crossed about as often as the two triangles it replaces)
+    comp = tg.fetch_segments(compact=True)
+    full = tg.fetch_segments()
+    assert all(np.array_equal(comp[k], full[k]) for k in api.SegmentColumns.KEYS)
+    sx, sy, sz = rt.plotdata.segment_lines(tg, uid=[1, tg.n_total_tracks])  # src/plot_recipes.jl:50-74 on two tracks
+    n1 = len(tg.tracks_by_uid[1].segments)
+    assert sx.shape[0] == 2 and sx.shape[1] == n1 + len(tg.tracks_by_uid[tg.n_total_tracks].segments)
+    assert np.array_equal(sx[0, :n1], full["px"][:n1]) and np.array_equal(sz[0, :n1], full["element"][:n1])
+    tx, ty = rt.plotdata.track_lines(tg)
+    assert tx.shape == (2, tg.n_total_tracks) and np.array_equal(tx[1], tg.track_data["q"][:, 0])
+    with pytest.raises(rt.RTError):
+        tg.neighbours()
+    with pytest.raises(rt.RTError):
+        tg.element_volumes()
+
+
 def test_resident_batch_guards_and_k_limit(pincell_model):
     """Track.segments refuses tracks whose batch is not resident (instead of indexing another batch's columns); k beyond
     RT_MAX_K is rejected instead of being clamped; k within it reaches the kNN fallback unchanged."""
