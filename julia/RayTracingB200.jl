@@ -102,13 +102,67 @@ function b200_trace!(t::TrackGenerator{T}) where {T}
 end
 
 """
-    b200_segmentize!(t::TrackGenerator; k=5, rtol=√eps)
+    B200Segments{T} <: AbstractVector{Segment{T}}
 
-Device version of `segmentize!` (trackgenerator.jl:357-369): count pass → scan → fill pass (+ fused
-`fill_volumes`), then the SoA records are materialised as the reference's `Vector{Segment}` per track.
-For meshes whose segments do not fit host memory use `rt_segments_device` / the batch callback instead.
+Lazy view of one track's segments over the SoA columns the device produced: a `Segment` (src/segment.jl:23-29) is only built when
+it is indexed, so a `segmentize!` of 5e7 segments does not allocate 5e7 `Segment`s with 5e7 empty `τ` vectors up front.  The
+columns are the COMPACT download (include/rt_b200.h: rt_segments_download_compact): `q`, `ℓ`, `element` crossed the bus, the entry
+point is the exit point of the segment before it (`p[i] = q[i-1]`) except at the positions of the exception list, which the
+constructor of the columns has already patched into `px`, `py` lazily per track (see `_b200_track_p`).
 """
-function b200_segmentize!(t::TrackGenerator{T}; k::Int=5, rtol::Real=Base.rtoldefault(T)) where {T}
+struct B200Segments{T} <: AbstractVector{Segment{T}}
+    cols::Any          # B200Columns
+    lo::Int            # 1-based position of the track's first segment in the columns
+    n::Int
+end
+Base.size(v::B200Segments) = (v.n,)
+function Base.getindex(v::B200Segments{T}, i::Int) where {T}
+    @boundscheck checkbounds(v, i)
+    c = v.cols
+    s = v.lo + i - 1
+    px, py = _b200_p(c, s)
+    return Segment(Point2D(px, py), Point2D(c.qx[s], c.qy[s]), c.len[s], Vector{T}(), c.element[s])
+end
+
+"the columns of one `segmentize!`: what crossed the bus plus the (sorted) exception list"
+struct B200Columns
+    qx::Vector{Float64}
+    qy::Vector{Float64}
+    len::Vector{Float64}
+    element::Vector{Int32}
+    exc_index::Vector{Int64}   # sorted, 1-based positions whose p is NOT the preceding q (first segment of a track, ...)
+    exc_px::Vector{Float64}
+    exc_py::Vector{Float64}
+end
+function _b200_p(c::B200Columns, s::Int)
+    k = searchsortedfirst(c.exc_index, s)
+    (k <= length(c.exc_index) && c.exc_index[k] == s) && return c.exc_px[k], c.exc_py[k]
+    return c.qx[s-1], c.qy[s-1]
+end
+
+const _B200_COLS = IdDict{Any,Tuple{B200Columns,Vector{Int64}}}()   # per TrackGenerator: columns + offsets
+
+"""
+    b200_segments(t::TrackGenerator, uid) -> B200Segments
+
+Lazy `Vector{Segment}`-like view of track `uid` after `b200_segmentize!(t; materialize=false)`.
+"""
+function b200_segments(t::TrackGenerator{T}, uid::Integer) where {T}
+    cols, off = _B200_COLS[t.tracks_by_uid]
+    return B200Segments{T}(cols, off[uid] + 1, off[uid+1] - off[uid])
+end
+
+"""
+    b200_segmentize!(t::TrackGenerator; k=5, rtol=√eps, materialize=true)
+
+Device version of `segmentize!` (trackgenerator.jl:357-369): walk (count + record) → scan → evaluation (+ fused `fill_volumes`).
+The records come back over the thin wire (28 bytes per segment).  With `materialize=true` every `track.segments` is refilled with
+the reference's own `Segment` objects, exactly as `_segmentize_track!` leaves them (one `Segment` + one empty `τ` per segment:
+fine for the reference's own problem sizes, seconds for 5e7 segments); with `materialize=false` they stay empty and
+`b200_segments(t, uid)` gives a lazy view instead.  For meshes whose segments do not fit host memory use `rt_segments_device` /
+the batch callback.
+"""
+function b200_segmentize!(t::TrackGenerator{T}; k::Int=5, rtol::Real=Base.rtoldefault(T), materialize::Bool=true) where {T}
     @unpack tracks_by_uid, azimuthal_quadrature, volumes = t
     !isassigned(tracks_by_uid, 1) && error("Segmentation is intended after tracing. Please, " *
                                            "call `trace!` first!")
@@ -119,20 +173,41 @@ function b200_segmentize!(t::TrackGenerator{T}; k::Int=5, rtol::Real=Base.rtolde
          Ptr{Int64}, Ptr{Int64}, Ptr{Int32}),
         ctx, Float64(t.tiny_step), Int32(k), Float64(rtol), Int32(MAX_ITER), azimuthal_quadrature.δs, UInt32(0),
         C_NULL, C_NULL, nseg, bad, st)
-    _b200_check(ctx, rc)                                      # RT_ERR_TRACK carries the reference's error text + uid
+    if rc != 0
+        # every rank of a communicator enters the all-reduce once per segmentize!, also the one that is about to throw
+        # (include/rt_b200.h, rt_volumes): keep the message of rt_segmentize, join, then raise it
+        msg = unsafe_string(ccall((:rt_last_error, LIBRT_B200), Cstring, (Ptr{Cvoid},), ctx))
+        ccall((:rt_volumes, LIBRT_B200), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx, C_NULL)
+        error(msg)                                            # RT_ERR_TRACK carries the reference's error text + uid
+    end
     n = t.n_total_tracks; S = nseg[]
     off = Vector{Int64}(undef, n + 1)
     _b200_check(ctx, ccall((:rt_segment_offsets, LIBRT_B200), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int32}), ctx, off, C_NULL))
-    px = Vector{Float64}(undef, S); py = similar(px); qx = similar(px); qy = similar(px); len = similar(px)
-    el = Vector{Int32}(undef, S)
-    _b200_check(ctx, ccall((:rt_segments_download, LIBRT_B200), Cint,
-        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
-        ctx, px, py, qx, qy, len, el))
+    qx = Vector{Float64}(undef, S); qy = similar(qx); len = similar(qx); el = Vector{Int32}(undef, S)
+    cap = 4n + S ÷ 64 + 1024
+    ei = Vector{Int64}(undef, cap); ex = Vector{Float64}(undef, cap); ey = similar(ex); ne = Ref{Int64}(0)
+    rc = ccall((:rt_segments_download_compact, LIBRT_B200), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+        ctx, qx, qy, len, el, cap, ei, ex, ey, ne)
+    if rc == -10                                              # RT_ERR_NOMEM: more exceptions than room; the call reported how many
+        cap = ne[] + 1024; resize!(ei, cap); resize!(ex, cap); resize!(ey, cap)
+        rc = ccall((:rt_segments_download_compact, LIBRT_B200), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+            ctx, C_NULL, C_NULL, C_NULL, C_NULL, cap, ei, ex, ey, ne)
+    end
+    _b200_check(ctx, rc)
+    resize!(ei, ne[]); resize!(ex, ne[]); resize!(ey, ne[])
+    o = sortperm(ei)
+    cols = B200Columns(qx, qy, len, el, ei[o] .+ 1, ex[o], ey[o])   # (the ABI's indices are 0-based positions)
+    _B200_COLS[tracks_by_uid] = (cols, off)
     for uid in 1:n
         segs = tracks_by_uid[uid].segments
-        empty!(segs); sizehint!(segs, off[uid+1] - off[uid])
+        empty!(segs)
+        materialize || continue
+        sizehint!(segs, off[uid+1] - off[uid])
         for s in off[uid]+1:off[uid+1]
-            push!(segs, Segment(Point2D(px[s], py[s]), Point2D(qx[s], qy[s]), len[s], Vector{T}(), el[s]))
+            px, py = _b200_p(cols, s)
+            push!(segs, Segment(Point2D(px, py), Point2D(qx[s], qy[s]), len[s], Vector{T}(), el[s]))
         end
     end
     _b200_check(ctx, ccall((:rt_volumes, LIBRT_B200), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx, volumes))

@@ -23,12 +23,14 @@
 
 namespace rt {
 
+// one warp per block: a block's slot is free again the moment its chunk is done (measured 1 % better than 4 warps per block,
+// 3 % better than 8: profiles/r2_block_sizes.txt)
 #ifndef RT_EVAL3_THREADS
-#define RT_EVAL3_THREADS 128
+#define RT_EVAL3_THREADS 32
 #endif
 constexpr int kEval3Threads = RT_EVAL3_THREADS;
 #ifndef RT_EVAL3_MIN_BLOCKS
-#define RT_EVAL3_MIN_BLOCKS 8
+#define RT_EVAL3_MIN_BLOCKS 32
 #endif
 
 // intersection(track, L) (src/intersection.jl:127-138) through the shared-reciprocal division; `redo` is set when a quotient did

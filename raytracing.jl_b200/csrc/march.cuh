@@ -17,7 +17,7 @@
 namespace rt {
 
 #ifndef RT_MARCH_THREADS
-#define RT_MARCH_THREADS 128
+#define RT_MARCH_THREADS 64
 #endif
 constexpr int kMarchThreads = RT_MARCH_THREADS;
 #ifndef RT_MARCH_WAIT
@@ -25,7 +25,7 @@ constexpr int kMarchThreads = RT_MARCH_THREADS;
 #endif
 constexpr int kMarchWait = RT_MARCH_WAIT;
 #ifndef RT_MARCH_MIN_BLOCKS
-#define RT_MARCH_MIN_BLOCKS 8
+#define RT_MARCH_MIN_BLOCKS 16
 #endif
 
 struct MarchState {
