@@ -130,6 +130,9 @@ struct rt_ctx {
     double tau_ms = 0.0;
     cudaEvent_t ev2[2] = {nullptr, nullptr};
     int opt_order_grid = 32;           // G x G tiles (0: identity order)
+    const int *order_eval = nullptr;   // execution order of the evaluation (plain Morton order)
+    int opt_order_classes = 3;         // duration bins of the walk's launch order, longest units first (walk.cuh k_unit_keys); 0: spatial order
+                                       // only.  Three bins: finer ones cost more in locality than they gain in balance (profiles/r2_walk_order.txt)
     int n_sm = 148;
     long long n_units = 0;
     double opt_chunk_segments = 128.0;              // minimum expected segments per chunk
@@ -957,6 +960,7 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
             WalkParams PE = P;
             PE.lmin = lmin_eval;
             PE.cancel = (const int *)ctx->b_guard.p;
+            if (PE.ch.order) PE.ch.order = ctx->order_eval;
             tic(ctx, 4);
             k_eval3<<<blocks_for((PE.unit_end - PE.unit_begin) * 32 * 32, kEval3Threads), kEval3Threads, 0, st>>>(PE);
             EvalParams E{};
@@ -1060,6 +1064,7 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
             }
             WalkParams PE = P;
             PE.lmin = lmin_eval;
+            if (PE.ch.order) PE.ch.order = ctx->order_eval;
             tic(ctx, 4);
             if (nseg_b > 0)
                 k_eval3<<<blocks_for((PE.unit_end - PE.unit_begin) * 32 * 32, kEval3Threads), kEval3Threads, 0, st>>>(PE);
@@ -1178,7 +1183,7 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         key.gen = ctx->trace_gen;
         key.chunk_len = chunk_len;
         key.band = ctx->opt_band_chunks;
-        key.order_grid = ctx->opt_order_grid;
+        key.order_grid = ctx->opt_order_grid + 1000 * ctx->opt_order_classes;
         key.n = n;
         const bool reuse = ctx->opt_plan_cache && key == ctx->plan_key && ctx->n_units > 0;
         ChunkPlan &ch = P.ch;
@@ -1223,25 +1228,34 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         ch.sum = cd + 2 * nc;
         P.unit_begin = 0;
         P.unit_end = n_units;
-        // ---- spatial execution order (counting sort of the units by Morton tile)
+        // ---- execution orders (counting sorts of the units): the walk launches the units that start a track first and the short
+        // ones last, in Morton order of their tiles inside each class; the evaluation, whose warps live for microseconds, keeps
+        // the plain Morton order
         ch.order = nullptr;
+        ctx->order_eval = nullptr;
         if (ctx->opt_order_grid > 0 && n_units < (1LL << 31)) {
+            const bool two = ctx->opt_order_classes != 0;
             if (!reuse) {
                 int G = std::min(ctx->opt_order_grid, 256);
                 int gp = 1;
                 while (gp < G) gp <<= 1;
-                size_t n_keys = (size_t)gp * gp;
-                CK(ensure(ctx->b_order, sizeof(int) * (size_t)n_units));
+                CK(ensure(ctx->b_order, sizeof(int) * (size_t)n_units * (two ? 2 : 1)));
                 CK(ensure(ctx->b_okeys, sizeof(int) * (size_t)n_units));
-                CK(ensure(ctx->b_ohist, sizeof(int) * (3 * n_keys + 1)));
-                int *hist = (int *)ctx->b_ohist.p, *ptrs = hist + n_keys, *cursor = ptrs + n_keys + 1;
-                CK(cudaMemsetAsync(hist, 0, sizeof(int) * (3 * n_keys + 1), st));
-                k_unit_keys<<<blocks_for(n_units, 256), 256, 0, st>>>(P, G, (int *)ctx->b_okeys.p, hist);
-                CK((exclusive_scan<int, int>(ctx, hist, ptrs, (long long)n_keys)));
-                k_unit_scatter<<<blocks_for(n_units, 256), 256, 0, st>>>(n_units, (const int *)ctx->b_okeys.p, ptrs, cursor, (int *)ctx->b_order.p);
-                launches += 5;
+                for (int pass = 0; pass < (two ? 2 : 1); ++pass) {
+                    const int classes = (two && pass == 0 && isfinite(chunk_len)) ? ctx->opt_order_classes : 1;
+                    size_t n_keys = (size_t)gp * gp * classes;
+                    CK(ensure(ctx->b_ohist, sizeof(int) * (3 * n_keys + 1)));
+                    int *hist = (int *)ctx->b_ohist.p, *ptrs = hist + n_keys, *cursor = ptrs + n_keys + 1;
+                    CK(cudaMemsetAsync(hist, 0, sizeof(int) * (3 * n_keys + 1), st));
+                    k_unit_keys<<<blocks_for(n_units, 256), 256, 0, st>>>(P, G, classes, gp * gp, chunk_len, (int *)ctx->b_okeys.p, hist);
+                    CK((exclusive_scan<int, int>(ctx, hist, ptrs, (long long)n_keys)));
+                    k_unit_scatter<<<blocks_for(n_units, 256), 256, 0, st>>>(n_units, (const int *)ctx->b_okeys.p, ptrs, cursor,
+                                                                            (int *)ctx->b_order.p + (size_t)pass * n_units);
+                    launches += 5;
+                }
             }
             ch.order = (const int *)ctx->b_order.p;
+            ctx->order_eval = two ? (const int *)ctx->b_order.p + n_units : ch.order;
         }
         if (!reuse) ctx->plan_key = key;
         // ---- seeds, count pass, per-track fix-up
@@ -2059,6 +2073,8 @@ extern "C" int rt_set_option(rt_ctx *ctx, const char *name, double value) {
         ctx->opt_debug_clear_pool = value != 0.0;
     else if (n == "band_cost" && value >= 0.0)
         ctx->opt_band_cost = value;
+    else if (n == "order_classes" && value >= 0.0 && value <= 64.0)
+        ctx->opt_order_classes = (int)value;
     else if (n == "plan_cache")
         ctx->opt_plan_cache = value != 0.0;
     else if (n == "optimistic")
