@@ -431,6 +431,8 @@ __global__ void __launch_bounds__(kMarchThreads, RT_MARCH_MIN_BLOCKS) k_march(co
         P.ch.count[S.cidx] = active ? nseg : 0;
         P.ch.sum[S.cidx] = 0.0;
         P.ch.endcode[S.cidx] = active ? (endcode | (S.status << 8)) : (END_HANDOFF | (0 << 8));
+    } else {
+        P.ch.count[S.cidx] = 0;  // (a slot no track owns: the evaluation requests its count before it knows that)
     }
     if (P.counters) {
         unsigned long long v = active ? (unsigned long long)(nseg - S.n_litpush) : 0ull;

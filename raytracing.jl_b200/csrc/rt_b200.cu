@@ -1208,6 +1208,10 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         CK(ensure(ctx->b_unit_block, sizeof(int) * (size_t)n_units));
         CK(ensure(ctx->b_ch_i, sizeof(int) * 5 * nc));
         CK(ensure(ctx->b_ch_d, sizeof(double) * 3 * nc));
+        if (!reuse) {  // (slots no track owns are never written by the kernels, but the evaluation requests them before it knows that)
+            CK(cudaMemsetAsync(ctx->b_ch_i.p, 0, sizeof(int) * 5 * nc, st));
+            CK(cudaMemsetAsync(ctx->b_ch_d.p, 0, sizeof(double) * 3 * nc, st));
+        }
         if (!reuse)
             k_fill_units<<<blocks_for(n_blocks, 128), 128, 0, st>>>(n_blocks, (const long long *)ctx->b_unit_base.p,
                                                                      (int *)ctx->b_unit_block.p);

@@ -296,6 +296,8 @@ __global__ void __launch_bounds__(kTopoThreads, RT_TOPO_MIN_BLOCKS) k_topo(const
         P.ch.count[cidx] = active ? nseg : 0;
         P.ch.sum[cidx] = 0.0;
         P.ch.endcode[cidx] = active ? (endcode | (status << 8)) : (END_HANDOFF | (0 << 8));
+    } else if (REC) {
+        P.ch.count[cidx] = 0;  // (a slot no track owns: the evaluation requests its count before it knows that)
     }
     if (P.counters) {
         unsigned long long v = active ? (unsigned long long)(nseg - n_litpush) : 0ull;
