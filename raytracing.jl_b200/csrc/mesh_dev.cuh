@@ -50,6 +50,7 @@ struct DevMesh {
     double g0x, g0y, gh, ginv;
     const int *grid_ptrs;   // gx*gy + 1
     const int *grid_nodes;  // node ids binned
+    const int *cell_bin;    // gx*gy: a cell whose centroid lies in the bin (-1: none) -- entry point of the seed location walk
     double bbmin[2], bbmax[2];
 };
 
@@ -357,6 +358,51 @@ __global__ void k_grid_fill(DevMesh m, const int *ptrs, int *cursor, int *nodes)
     int b = grid_bin(m, p.x, p.y);
     int pos = atomicAdd(&cursor[b], 1);
     nodes[ptrs[b] + pos] = i;
+}
+
+// ---- cheap point location for the seeds of the sub-track chunks (k_seed) ------------------------------------------------------
+// A seed only has to name SOME cell the serial walk pushes near the nominal seed point (DESIGN.md "chunks": exactness never
+// depends on the seed, only efficiency does), so it does not need the reference's find_element with its nearest-node search
+// and tolerant barycentric tests: jump to a cell whose centroid lies in the point's grid bin and walk towards the point through
+// the neighbour table, deciding every step from the signs of the three edge functions (no division).  Returns the cell that
+// contains (x, y), or -1 when the walk does not get there (empty bin, hole, too far): the caller falls back to find_element.
+__global__ void k_cell_bins(DevMesh m, const CellRec *cells, int *cell_bin) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m.n_cells) return;
+    const CellRec &r = cells[c];
+    const double cx = (r.vx[0] + r.vx[1] + r.vx[2]) / 3.0, cy = (r.vy[0] + r.vy[1] + r.vy[2]) / 3.0;
+    atomicMax(&cell_bin[grid_bin(m, cx, cy)], c);
+}
+
+__device__ __forceinline__ int locate_by_walk(const DevMesh &m, double x, double y) {
+    int c = m.cell_bin[grid_bin(m, x, y)];
+    for (int it = 0; it < 16 && c >= 0; ++it) {
+        const CellRec &r = m.cells[c];
+        const double x1 = r.vx[0], y1 = r.vy[0], x2 = r.vx[1], y2 = r.vy[1], x3 = r.vx[2], y3 = r.vy[2];
+        const double d = (x2 - x1) * (y3 - y1) - (x3 - x1) * (y2 - y1);  // twice the signed area: orientation of the stored nodes
+        double e0 = (x2 - x1) * (y - y1) - (x - x1) * (y2 - y1);         // edge k = (v_k, v_k+1): same sign as d on the inner side
+        double e1 = (x3 - x2) * (y - y2) - (x - x2) * (y3 - y2);
+        double e2 = (x1 - x3) * (y - y3) - (x - x3) * (y1 - y3);
+        if (d < 0.0) {
+            e0 = -e0;
+            e1 = -e1;
+            e2 = -e2;
+        }
+        int k = -1;
+        double mn = 0.0;
+        if (e0 < mn) {
+            mn = e0;
+            k = 0;
+        }
+        if (e1 < mn) {
+            mn = e1;
+            k = 1;
+        }
+        if (e2 < mn) k = 2;
+        if (k < 0) return c;
+        c = r.nbr[k];
+    }
+    return -1;
 }
 
 // ------------------------------------------------------------------------------------------------

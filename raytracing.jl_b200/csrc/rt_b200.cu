@@ -88,6 +88,7 @@ struct rt_ctx {
     cudaEvent_t ev_aux = nullptr;
     bool area_valid = false;
     long long *h_pin = nullptr;  // page-locked scratch for the small device->host read-backs of rt_segmentize (16 words)
+    DevBuf b_cell_bin;
     DevBuf b_scratch, b_gcounts, b_gcursor;  // rt_mesh_upload staging (kept between uploads)
     DevBuf b_verify, b_tsum;    // self-verifying pipelines: verification flag, per-track length sums
     DevBuf b_pool, b_pool_next, b_pool_cursor;  // single-walk pipeline: record blocks (walk.cuh kRecBlock), chain, cursor
@@ -261,7 +262,7 @@ extern "C" void rt_destroy(rt_ctx *ctx) {
                      &ctx->b_twin,    &ctx->b_he,         &ctx->b_node_reach,
                      &ctx->b_nch,     &ctx->b_blk_chunks, &ctx->b_unit_base, &ctx->b_unit_block, &ctx->b_ch_i, &ctx->b_ch_d,
                      &ctx->b_order,   &ctx->b_okeys,      &ctx->b_ohist,     &ctx->b_verify,    &ctx->b_tsum,
-                     &ctx->b_scratch, &ctx->b_gcounts,   &ctx->b_gcursor,
+                     &ctx->b_scratch, &ctx->b_gcounts,   &ctx->b_gcursor,   &ctx->b_cell_bin,
                      &ctx->b_omega,   &ctx->b_sigma,     &ctx->b_tau,
                      &ctx->b_pool,    &ctx->b_pool_next, &ctx->b_pool_cursor,
                      &ctx->b_area,    &ctx->b_factor,    &ctx->b_layout,    &ctx->b_vol_alt,  &ctx->b_guard,  &ctx->b_exc};
@@ -458,6 +459,13 @@ extern "C" int rt_mesh_upload(rt_ctx *ctx, int32_t n_nodes, const double *xy, in
     k_grid_count<<<blocks_for(n_nodes, 256), 256, 0, st>>>(m, (int *)counts.p);
     CK((exclusive_scan<int, int>(ctx, (const int *)counts.p, (int *)ctx->b_grid_ptrs.p, (long long)n_bins)));
     k_grid_fill<<<blocks_for(n_nodes, 256), 256, 0, st>>>(m, m.grid_ptrs, (int *)cursor.p, (int *)ctx->b_grid_nodes.p);
+    m.cell_bin = nullptr;
+    if (!mixed) {  // entry points of the seed location walk (k_seed)
+        CK(ensure(ctx->b_cell_bin, sizeof(int) * n_bins));
+        CK(cudaMemsetAsync(ctx->b_cell_bin.p, 0xff, sizeof(int) * n_bins, st));
+        k_cell_bins<<<blocks_for(n_cells, 256), 256, 0, st>>>(m, (const CellRec *)ctx->b_cells.p, (int *)ctx->b_cell_bin.p);
+        m.cell_bin = (const int *)ctx->b_cell_bin.p;
+    }
     CK(cudaGetLastError());
     MeshScalars sc;
     CK(cudaMemcpyAsync(&sc, ctx->b_sc.p, sizeof(sc), cudaMemcpyDeviceToHost, st));

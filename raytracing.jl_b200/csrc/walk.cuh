@@ -281,7 +281,8 @@ __global__ void __launch_bounds__(128) k_seed(const __grid_constant__ WalkParams
     double s = chunk_start(P.ch.layout[t], P.t.len[t], n, j);
     double x = P.t.px[t] + s * P.ang.cosp[az], y = P.t.py[t] + s * P.ang.sinp[az];
     bool right = P.ang.phi[az] < kPi / 2;
-    int c = find_element(m, x, y, 2, nullptr);
+    int c = locate_by_walk(m, x, y);  // (any cell near the seed point that the walk pushes will do: no need for the reference's search)
+    if (c < 0) c = find_element(m, x, y, 2, nullptr);
     if (c < 0) return;
     const CellRec &r = m.cells[c];
     if (!isfinite(r.clear)) return;  // degenerate cells never seed
