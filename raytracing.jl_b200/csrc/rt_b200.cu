@@ -77,7 +77,12 @@ struct rt_ctx {
 
     // segmentation
     bool segmented = false;
-    DevBuf b_count, b_status, b_offsets, b_tile, b_vol, b_voln, b_counters, b_bad;
+    DevBuf b_count, b_status, b_offsets, b_tile, b_vol, b_voln;
+    // control words of one rt_segmentize in ONE 64-byte block: reset with one copy, read back with one copy (every separate
+    // memset / memcpy is a few microseconds of an otherwise idle GPU at the start and at the end of a call)
+    //   [0..3] counters (fast transitions, literal iterations, nn / knn queries)  [4] first bad track  [5] verify flag | guard flag << 32
+    DevBuf b_ctrl;
+    std::vector<double> h_delta;       // delta_eff as last uploaded (the upload is skipped when the caller passes the same values)
     DevBuf b_layout;  // per-track chunk layout (walk.cuh ChunkLayout)
     DevBuf b_nch, b_blk_chunks, b_unit_base, b_unit_block, b_ch_i, b_ch_d;  // chunk plan (walk.cuh ChunkPlan)
     DevBuf b_order, b_okeys, b_ohist;  // spatial execution order of the units
@@ -90,7 +95,7 @@ struct rt_ctx {
     long long *h_pin = nullptr;  // page-locked scratch for the small device->host read-backs of rt_segmentize (16 words)
     DevBuf b_cell_bin;
     DevBuf b_scratch, b_gcounts, b_gcursor;  // rt_mesh_upload staging (kept between uploads)
-    DevBuf b_verify, b_tsum;    // self-verifying pipelines: verification flag, per-track length sums
+    DevBuf b_tsum;    // self-verifying pipelines: per-track length sums
     DevBuf b_pool, b_pool_next, b_pool_cursor;  // single-walk pipeline: record blocks (walk.cuh kRecBlock), chain, cursor
     int count_batches = 0;             // single-walk pipeline: how many uid batches the count walk needed (info)
     // The chunk plan (k_plan_chunks .. k_unit_scatter) depends on the tracks, the mesh density and the chunk options only: it is
@@ -118,7 +123,7 @@ struct rt_ctx {
     unsigned long long fit_gen = ~0ULL;  // trace generation whose previous call fitted the Segment columns and the pool in ONE batch
     bool deferred_total = false;
     bool redo_careful = false;         // the repeat asked for by the optimistic path (not a failed verification)
-    DevBuf b_guard;
+
     int opt_band_chunks = 1;           // 8x shorter chunks for tracks that run along the bounding box (walk.cuh k_plan_chunks)
     int opt_march = 1;                 // single-walk pipeline: k_march (register-resident loop) instead of k_topo<2>
     long long opt_pool_slots = 0;      // test hook: at most this many chunk slots per count batch (0: as many as fit)
@@ -167,6 +172,12 @@ struct rt_ctx {
     bool ev_vol_used[2] = {false, false};
     int voln_ready = -1;                                    // index of the event that marks b_voln complete (-1: main stream)
 };
+
+static inline unsigned long long *d_counters(rt_ctx *c) { return (unsigned long long *)c->b_ctrl.p; }
+static inline unsigned long long *d_bad(rt_ctx *c) { return (unsigned long long *)c->b_ctrl.p + 4; }
+static inline int *d_verify(rt_ctx *c) { return (int *)((unsigned long long *)c->b_ctrl.p + 5); }
+static inline int *d_guard(rt_ctx *c) { return (int *)((unsigned long long *)c->b_ctrl.p + 5) + 1; }
+constexpr int kPinWords = 32, kPinCtrlInit = 16, kPinCtrl = 24;  // page-locked scratch: template and read-back of the control block
 
 static int fail(rt_ctx *c, int code, const char *fmt, ...) {
     char buf[512];
@@ -234,7 +245,7 @@ extern "C" int rt_create(rt_ctx **out, int device) {
         delete ctx;
         return RT_ERR_CUDA;
     }
-    if (cudaHostAlloc((void **)&ctx->h_pin, 16 * sizeof(long long), cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc((void **)&ctx->h_pin, kPinWords * sizeof(long long), cudaHostAllocDefault) != cudaSuccess) {
         delete ctx;
         return RT_ERR_NOMEM;
     }
@@ -258,14 +269,14 @@ extern "C" void rt_destroy(rt_ctx *ctx) {
                      &ctx->b_edges,   &ctx->b_qual,       &ctx->b_bdist,    &ctx->b_sc,      &ctx->b_grid_ptrs, &ctx->b_grid_nodes,
                      &ctx->b_ang_d,   &ctx->b_ang_i,      &ctx->b_trk_d,    &ctx->b_trk_i,   &ctx->b_trk_l,   &ctx->b_trk_c,
                      &ctx->b_err,     &ctx->b_count,      &ctx->b_status,   &ctx->b_offsets, &ctx->b_tile,    &ctx->b_vol,
-                     &ctx->b_voln,    &ctx->b_counters,   &ctx->b_bad,      &ctx->b_seg_d,   &ctx->b_seg_e,
+                     &ctx->b_voln,    &ctx->b_ctrl,       &ctx->b_seg_d,   &ctx->b_seg_e,
                      &ctx->b_twin,    &ctx->b_he,         &ctx->b_node_reach,
                      &ctx->b_nch,     &ctx->b_blk_chunks, &ctx->b_unit_base, &ctx->b_unit_block, &ctx->b_ch_i, &ctx->b_ch_d,
-                     &ctx->b_order,   &ctx->b_okeys,      &ctx->b_ohist,     &ctx->b_verify,    &ctx->b_tsum,
+                     &ctx->b_order,   &ctx->b_okeys,      &ctx->b_ohist,     &ctx->b_tsum,
                      &ctx->b_scratch, &ctx->b_gcounts,   &ctx->b_gcursor,   &ctx->b_cell_bin,
                      &ctx->b_omega,   &ctx->b_sigma,     &ctx->b_tau,
                      &ctx->b_pool,    &ctx->b_pool_next, &ctx->b_pool_cursor,
-                     &ctx->b_area,    &ctx->b_factor,    &ctx->b_layout,    &ctx->b_vol_alt,  &ctx->b_guard,  &ctx->b_exc};
+                     &ctx->b_area,    &ctx->b_factor,    &ctx->b_layout,    &ctx->b_vol_alt,  &ctx->b_exc};
     for (DevBuf *b : all) release(*b);
     for (int ph = 0; ph < 6; ++ph)
         for (int q = 0; q < 2; ++q)
@@ -953,8 +964,7 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
         if (!multi && !cb && ctx->cap_cfg == 0 && ctx->opt_optimistic && !ctx->skip_optimistic_once && ctx->fit_gen == ctx->trace_gen &&
             ctx->b_seg_d.p && ctx->cap > 0) {
             // ---- optimistic evaluation: no host round trip between the walk and the evaluation (see rt_ctx::opt_optimistic)
-            CK(ensure(ctx->b_guard, sizeof(int)));
-            k_guard<<<1, 1, 0, st>>>((const long long *)ctx->b_offsets.p + e, base, ctx->cap, P.pool_cursor, P.pool_blocks, (int *)ctx->b_guard.p);
+            k_guard<<<1, 1, 0, st>>>((const long long *)ctx->b_offsets.p + e, base, ctx->cap, P.pool_cursor, P.pool_blocks, d_guard(ctx));
             P.opx = ctx->s_px;
             P.opy = ctx->s_py;
             P.oqx = ctx->s_qx;
@@ -967,7 +977,7 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
             P.offset_base = base;
             WalkParams PE = P;
             PE.lmin = lmin_eval;
-            PE.cancel = (const int *)ctx->b_guard.p;
+            PE.cancel = d_guard(ctx);
             if (PE.ch.order) PE.ch.order = ctx->order_eval;
             tic(ctx, 4);
             k_eval3<<<blocks_for((PE.unit_end - PE.unit_begin) * 32 * 32, kEval3Threads), kEval3Threads, 0, st>>>(PE);
@@ -989,10 +999,7 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
             launches += 3;
             CK(cudaGetLastError());
             toc(ctx, 4);
-            ctx->h_pin[2] = 0;
-            ctx->h_pin[10] = 0;
-            CK(cudaMemcpyAsync(&ctx->h_pin[2], ctx->b_verify.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(&ctx->h_pin[10], ctx->b_guard.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            // (verification and guard flags come back with the control block at the end of the call, segmentize_once)
             ctx->res_trk_begin = b;
             ctx->res_trk_end = e;
             ctx->res_off_base = base;
@@ -1089,7 +1096,7 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
             ctx->res_nseg = nseg_b;
             toc(ctx, 4);
             ctx->h_pin[2] = 0;
-            CK(cudaMemcpyAsync(&ctx->h_pin[2], ctx->b_verify.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&ctx->h_pin[2], d_verify(ctx), sizeof(int), cudaMemcpyDeviceToHost, st));
             if (!cb && !multi && !split) {
                 // one batch, nobody waits for it: the verification flag is read with the final read-back of the call
                 // (segmentize_once), which saves one host synchronisation per call; the fill time is collected lazily
@@ -1145,10 +1152,10 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
     *bad_out = ~0ULL;
     if (want_vol) CK(cudaMemsetAsync(ctx->vol_acc, 0, sizeof(double) * ((size_t)m.n_cells + 1), st));  // (+1: the failed-rank flag of rt_volumes)
     size_t nn = (size_t)std::max<long long>(n, 1);
-    CK(cudaMemsetAsync(ctx->b_counters.p, 0, sizeof(unsigned long long) * 4, st));
-    CK(cudaMemsetAsync(ctx->b_bad.p, 0xff, sizeof(unsigned long long), st));
-    CK(cudaMemsetAsync(ctx->b_offsets.p, 0, sizeof(long long) * (nn + 1), st));
-    CK(cudaMemsetAsync(ctx->b_verify.p, 0, sizeof(int), st));
+    for (int q = 0; q < 8; ++q) ctx->h_pin[kPinCtrlInit + q] = 0;
+    ctx->h_pin[kPinCtrlInit + 4] = -1LL;  // "no bad track"
+    CK(cudaMemcpyAsync(ctx->b_ctrl.p, &ctx->h_pin[kPinCtrlInit], 64, cudaMemcpyHostToDevice, st));
+    if (n == 0) CK(cudaMemsetAsync(ctx->b_offsets.p, 0, sizeof(long long) * (nn + 1), st));  // (otherwise the scan writes all n + 1 entries)
 
     WalkParams P{};
     P.m = m;
@@ -1169,8 +1176,8 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
     P.count = (int *)ctx->b_count.p;
     P.status = (int *)ctx->b_status.p;
     P.offsets = (const long long *)ctx->b_offsets.p;
-    P.counters = (unsigned long long *)ctx->b_counters.p;
-    P.verify_fail = (int *)ctx->b_verify.p;
+    P.counters = d_counters(ctx);
+    P.verify_fail = d_verify(ctx);
     const bool count_only = (flags & RT_SEG_COUNT_ONLY) != 0;
     double launches = 0;
 
@@ -1294,7 +1301,7 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         ctx->res_trk_begin = ctx->res_trk_end = 0;
         ctx->res_off_base = 0;
         ctx->res_nseg = 0;
-        P.counters = (unsigned long long *)ctx->b_counters.p;
+        P.counters = d_counters(ctx);
         int next_mode = 1;
         int rc = segmentize_single(ctx, P, rtol, want_vol, cb, cb_user, attempt, verify_failed, &next_mode, &launches, est_total_segments,
                                    &deferred_verify);
@@ -1364,7 +1371,7 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         E.oelem = P.oelem;
         E.vol = P.vol;
         E.lmin = ctx->opt_debug_verify_fail ? INFINITY : P.lmin;
-        if (ctx->opt_debug_verify_fail && topo_count) CK(cudaMemsetAsync(ctx->b_verify.p, 1, 1, st));
+        if (ctx->opt_debug_verify_fail && topo_count) CK(cudaMemsetAsync(d_verify(ctx), 1, 1, st));
         E.verify_fail = P.verify_fail;
         E.status = P.status;
         E.tsum = P.tsum;
@@ -1417,7 +1424,7 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
             ctx->res_nseg = nseg_b;
             if (topo_count) {
                 ctx->h_pin[2] = 0;
-                CK(cudaMemcpyAsync(&ctx->h_pin[2], ctx->b_verify.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(&ctx->h_pin[2], d_verify(ctx), sizeof(int), cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
                 const int vf = (int)ctx->h_pin[2];
                 if (vf) {
@@ -1439,15 +1446,15 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
     }
     unsigned long long bad = ~0ULL;
     if (n > 0) {
-        k_first_bad<<<blocks_for(n, 256), 256, 0, st>>>((const int *)ctx->b_status.p, n, (unsigned long long *)ctx->b_bad.p);
+        k_first_bad<<<blocks_for(n, 256), 256, 0, st>>>((const int *)ctx->b_status.p, n, d_bad(ctx));
         launches += 1;
-        CK(cudaMemcpyAsync(&ctx->h_pin[3], ctx->b_bad.p, sizeof(bad), cudaMemcpyDeviceToHost, st));
     }
-    CK(cudaMemcpyAsync(&ctx->h_pin[4], ctx->b_counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&ctx->h_pin[kPinCtrl], ctx->b_ctrl.p, 64, cudaMemcpyDeviceToHost, st));  // counters, first bad track, flags: one copy
     CK(cudaStreamSynchronize(st));
+    const int flag_verify = (int)(ctx->h_pin[kPinCtrl + 5] & 0xffffffffLL), flag_guard = (int)((unsigned long long)ctx->h_pin[kPinCtrl + 5] >> 32);
     if (ctx->deferred_total) {  // optimistic evaluation: the total arrives only now
         ctx->deferred_total = false;
-        if ((int)ctx->h_pin[10]) {  // cancelled on the device (Segment columns or record pool too small): repeat on the careful path
+        if (flag_guard) {  // cancelled on the device (Segment columns or record pool too small): repeat on the careful path
             ctx->skip_optimistic_once = true;
             ctx->fit_gen = ~0ULL;
             ctx->redo_careful = true;
@@ -1457,13 +1464,13 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         ctx->total_segments = ctx->h_pin[1];
         ctx->res_nseg = ctx->h_pin[1];
     }
-    if (deferred_verify && (int)ctx->h_pin[2]) {
+    if (deferred_verify && flag_verify) {
         *verify_failed = true;
         return RT_OK;
     }
-    if (n > 0) bad = (unsigned long long)ctx->h_pin[3];
+    if (n > 0) bad = (unsigned long long)ctx->h_pin[kPinCtrl + 4];
     unsigned long long hc[4];
-    for (int q = 0; q < 4; ++q) hc[q] = (unsigned long long)ctx->h_pin[4 + q];
+    for (int q = 0; q < 4; ++q) hc[q] = (unsigned long long)ctx->h_pin[kPinCtrl + q];
     ctx->stats[0] += launches;
     for (int q = 0; q < 4; ++q) ctx->stats[1 + q] = (double)hc[q];
     *bad_out = bad;
@@ -1503,7 +1510,10 @@ extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rt
     }
     if (want_vol) {
         // (pageable source: the call returns once the n2 values are staged, no synchronisation needed before the caller reuses them)
-        CK(cudaMemcpyAsync((double *)ctx->b_ang_d.p + 6 * (size_t)n2, delta_eff, sizeof(double) * n2, cudaMemcpyHostToDevice, st));
+        if (!ctx->has_delta || ctx->h_delta.size() != (size_t)n2 || memcmp(ctx->h_delta.data(), delta_eff, sizeof(double) * n2) != 0) {
+            CK(cudaMemcpyAsync((double *)ctx->b_ang_d.p + 6 * (size_t)n2, delta_eff, sizeof(double) * n2, cudaMemcpyHostToDevice, st));
+            ctx->h_delta.assign(delta_eff, delta_eff + n2);
+        }
         ctx->has_delta = true;
         CK(ensure(ctx->b_vol, sizeof(double) * ((size_t)m.n_cells + 1)));
         ctx->vol_acc = (double *)ctx->b_vol.p;
@@ -1520,9 +1530,7 @@ extern "C" int rt_segmentize(rt_ctx *ctx, double tiny_step, int32_t k, double rt
     CK(ensure(ctx->b_count, sizeof(int) * nn));
     CK(ensure(ctx->b_status, sizeof(int) * nn));
     CK(ensure(ctx->b_offsets, sizeof(long long) * (nn + 1)));
-    CK(ensure(ctx->b_counters, sizeof(unsigned long long) * 4));
-    CK(ensure(ctx->b_bad, sizeof(unsigned long long)));
-    CK(ensure(ctx->b_verify, sizeof(int)));
+    CK(ensure(ctx->b_ctrl, 64));
 
     // the configured pipeline unless a flag asks for behaviour only the sequential kernels have
     int mode = (flags & (RT_SEG_SEQUENTIAL | RT_SEG_COUNT_ONLY)) ? 1 : ctx->opt_pipeline;

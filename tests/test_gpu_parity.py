@@ -406,6 +406,7 @@ def test_cfg4_full_size_pipelines_agree():
     n = tg.n_total_tracks
     ranges = [(int(u), int(u) + 40) for u in np.linspace(1, n - 40, 7)]
     keys = ("px", "py", "qx", "qy", "len", "element")
+    M64 = (1 << 64) - 1
     results = []
     for pipeline in (0, 1, 3):
         tg.set_option("pipeline", pipeline)
@@ -421,9 +422,10 @@ def test_cfg4_full_size_pipelines_agree():
                 hi = min(b.n_segments, lo + step)
                 # weights from the GLOBAL segment position: the sums do not depend on how a pipeline cuts the batches
                 w = (torch.arange(lo, hi, device="cuda", dtype=torch.int64) + int(b.offset_base)) % 1021 + 1
-                sums["element"] = sums.get("element", 0) + int((cols["element"][lo:hi].to(torch.int64) * w).sum())
+                # (the device sums wrap modulo 2^64, so the totals are kept modulo 2^64 too: independent of the batch cuts)
+                sums["element"] = (sums.get("element", 0) + int((cols["element"][lo:hi].to(torch.int64) * w).sum())) & M64
                 for k in keys[:5]:  # bit patterns, so that any differing bit changes the sum
-                    sums[k] = sums.get(k, 0) + int((cols[k][lo:hi].view(torch.int64) & 0xFFFFFFFF).mul_(w).sum())
+                    sums[k] = (sums.get(k, 0) + int((cols[k][lo:hi].view(torch.int64) & 0xFFFFFFFF).mul_(w).sum())) & M64
             chk.append(tuple(row))
             for (u0, u1) in ranges:
                 if b.uid_begin <= u0 and u1 <= b.uid_end:
@@ -439,7 +441,8 @@ def test_cfg4_full_size_pipelines_agree():
         assert [r[0] for r in chk[1:]] == [r[1] for r in chk[:-1]] and chk[0][0] == 1 and chk[-1][1] == n + 1  # batches tile the uids
         results.append((tg.n_segments, sums, tg.segment_offsets.copy(), tg.segment_status.copy(), slices))
     for other in results[1:]:
-        assert other[0] == results[0][0] and other[1] == results[0][1]
+        assert other[0] == results[0][0], (other[0], results[0][0])
+        assert other[1] == results[0][1], (other[1], results[0][1])
         assert np.array_equal(other[2], results[0][2]) and np.array_equal(other[3], results[0][3])
     # ---- the oracle on the sampled uid ranges and on every failing track
     off, status, slices = results[0][2], results[0][3], results[0][4]
@@ -728,7 +731,21 @@ def test_single_walk_pipeline_batches_and_pool_exhaustion():
     assert_volumes_close(otg, tg)
     from raytracing_jl_b200 import _lib as L
     L.check(tg._ctx, L.lib().rt_set_segment_capacity(tg._ctx, 5000))  # ... and evaluation sub-batches inside each of them
-    rt.segmentize_(tg, check=False)
+    import torch
+
+    got = {key: np.zeros_like(otg.seg[key]) for key in ("px", "py", "qx", "qy", "len", "element")}
+    cuts = []
+
+    def on_batch(b):  # EVERY batch of the stream, not only the resident last one
+        for key in got:
+            got[key][b.offset_base:b.offset_base + b.n_segments] = torch.as_tensor(getattr(b, key), device="cuda")[:b.n_segments].cpu().numpy()
+        cuts.append((b.uid_begin, b.uid_end))
+
+    rt.segmentize_(tg, check=False, on_batch=on_batch)
+    assert tg.info("count_batches") > 3 and len(cuts) > 3 * tg.info("count_batches")
+    assert cuts[0][0] == 1 and cuts[-1][1] == tg.n_total_tracks + 1 and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+    for key in got:
+        assert np.array_equal(got[key], otg.seg[key]), key
     assert tg.info("verify_fallbacks") == 0 and np.array_equal(tg.segment_offsets, off_all)
     n = tg.segments["px"].shape[0]
     assert 0 < n <= 5000
