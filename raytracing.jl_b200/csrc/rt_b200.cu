@@ -105,11 +105,9 @@ struct rt_ctx {
     struct PlanKey {
         unsigned long long gen = ~0ULL;
         double chunk_len = -1.0;
-        int band = -1, order_grid = -1, pieces = -1;
+        int band = -1, order_grid = -1;
         long long n = -1;
-        bool operator==(const PlanKey &o) const {
-            return gen == o.gen && chunk_len == o.chunk_len && band == o.band && order_grid == o.order_grid && pieces == o.pieces && n == o.n;
-        }
+        bool operator==(const PlanKey &o) const { return gen == o.gen && chunk_len == o.chunk_len && band == o.band && order_grid == o.order_grid && n == o.n; }
     } plan_key;
     bool plan_has_order = false;
     int opt_debug_clear_pool = 0;      // test hook (initcheck): zero the record pool before every walk, so that the evaluation's speculative
@@ -139,16 +137,6 @@ struct rt_ctx {
     cudaEvent_t ev2[2] = {nullptr, nullptr};
     int opt_order_grid = 32;           // G x G tiles (0: identity order)
     const int *order_eval = nullptr;   // execution order of the evaluation (plain Morton order)
-    // Pieces (walk.cuh PieceCuts): the steady-state call launches the walk of every piece on its own stream and the evaluations
-    // behind them on a stream of lower priority; the evaluation of the pieces that are done runs on the SMs the walk's last,
-    // long-lived warps leave idle (the walk kernel alone keeps the SMs busy for ~0.7 of its duration).
-    static constexpr int kMaxPieces = 8;
-    int opt_pieces = 1;
-    int prio_low = 0, prio_high = 0;
-    int n_pieces = 1;                  // of the cached plan
-    long long piece_blk[kMaxPieces + 1] = {0}, piece_unit[kMaxPieces + 1] = {0};
-    cudaStream_t piece_stream[kMaxPieces] = {nullptr}, eval_stream = nullptr;
-    cudaEvent_t ev_piece[kMaxPieces] = {nullptr}, ev_fork = nullptr, ev_join = nullptr;
     int opt_order_classes = 3;         // duration bins of the walk's launch order, longest units first (walk.cuh k_unit_keys); 0: spatial order
                                        // only.  Three bins: finer ones cost more in locality than they gain in balance (profiles/r2_walk_order.txt)
     int n_sm = 148;
@@ -227,16 +215,14 @@ static void release(DevBuf &b) {
 static inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 template <typename Tin, typename Tout>
-static cudaError_t exclusive_scan(rt_ctx *ctx, const Tin *in, Tout *out, long long n, Tout carry = Tout(0), cudaStream_t s = nullptr,
-                                  const Tout *carry_at = nullptr) {
-    if (!s) s = ctx->stream;
+static cudaError_t exclusive_scan(rt_ctx *ctx, const Tin *in, Tout *out, long long n, Tout carry = Tout(0)) {
     long long n_tiles = (n + kScanTile - 1) / kScanTile;
     cudaError_t e = ensure(ctx->b_tile, sizeof(Tout) * (size_t)n_tiles);
     if (e != cudaSuccess) return e;
     Tout *tiles = (Tout *)ctx->b_tile.p;
-    k_scan_tile_sums<Tin, Tout><<<(unsigned)n_tiles, kScanThreads, 0, s>>>(in, tiles, n);
-    k_scan_tile_offsets<Tout><<<1, kScanThreads, 0, s>>>(tiles, n_tiles);
-    k_scan_apply<Tin, Tout><<<(unsigned)n_tiles, kScanThreads, 0, s>>>(in, out, tiles, n, carry, carry_at);
+    k_scan_tile_sums<Tin, Tout><<<(unsigned)n_tiles, kScanThreads, 0, ctx->stream>>>(in, tiles, n);
+    k_scan_tile_offsets<Tout><<<1, kScanThreads, 0, ctx->stream>>>(tiles, n_tiles);
+    k_scan_apply<Tin, Tout><<<(unsigned)n_tiles, kScanThreads, 0, ctx->stream>>>(in, out, tiles, n, carry);
     return cudaGetLastError();
 }
 
@@ -253,12 +239,7 @@ extern "C" int rt_create(rt_ctx **out, int device) {
     ctx->device = device;
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (ctx->n_sm <= 0) ctx->n_sm = 148;
-    // the main stream (and the walk streams of the pieces) sit one priority level above the evaluation stream of the pieces
-    int prio_least = 0, prio_greatest = 0;
-    if (cudaSetDevice(device) == cudaSuccess) cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
-    ctx->prio_low = prio_least;
-    ctx->prio_high = prio_greatest < prio_least ? prio_least - 1 : prio_least;
-    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, ctx->prio_high) != cudaSuccess ||
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->tev[0]) != cudaSuccess || cudaEventCreate(&ctx->tev[1]) != cudaSuccess ||
         cudaEventCreate(&ctx->ev2[0]) != cudaSuccess || cudaEventCreate(&ctx->ev2[1]) != cudaSuccess) {
         delete ctx;
@@ -306,13 +287,6 @@ extern "C" void rt_destroy(rt_ctx *ctx) {
     }
     for (cudaEvent_t e : {ctx->ev_fill_done, ctx->ev_vol_free[0], ctx->ev_vol_free[1]})
         if (e) cudaEventDestroy(e);
-    for (int i = 0; i < rt_ctx::kMaxPieces; ++i) {
-        if (ctx->piece_stream[i]) cudaStreamDestroy(ctx->piece_stream[i]);
-        if (ctx->ev_piece[i]) cudaEventDestroy(ctx->ev_piece[i]);
-    }
-    if (ctx->eval_stream) cudaStreamDestroy(ctx->eval_stream);
-    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->ev_aux) cudaEventDestroy(ctx->ev_aux);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -824,7 +798,7 @@ __global__ void k_normalise(const double *in, double *out, int n, double denom) 
 
 // optimistic evaluation: does the batch fit the Segment columns and did the record pool hold every record?  (one thread)
 __global__ void k_guard(const long long *total_at, long long base, long long cap, const int *pool_cursor, int pool_blocks, int *cancel) {
-    if (*total_at - base > cap || *pool_cursor > pool_blocks) *cancel = 1;  // (reset with the control block at the start of the call)
+    *cancel = (*total_at - base > cap || *pool_cursor > pool_blocks) ? 1 : 0;
 }
 
 extern "C" int rt_set_segment_capacity(rt_ctx *ctx, int64_t max_segments_resident) {
@@ -959,112 +933,6 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
         const long long u0 = multi ? h_unit_base[(size_t)B0] : 0, u1 = multi ? h_unit_base[(size_t)B1] : n_units;
         const long long slots = (u1 - u0) * 32;
         ctx->count_batches += 1;
-        const bool optimistic = !multi && !cb && ctx->cap_cfg == 0 && ctx->opt_optimistic && !ctx->skip_optimistic_once &&
-                                ctx->fit_gen == ctx->trace_gen && ctx->b_seg_d.p && ctx->cap > 0;
-        if (optimistic && ctx->n_pieces > 1) {
-            // ---- optimistic evaluation in pieces (rt_ctx::opt_pieces): every piece's walk on its own stream, in launch order; the
-            // per-piece fix-up, scan (the running total stays on the device), guard, evaluation and track status follow on ONE
-            // stream of lower priority, so the evaluation of piece i runs where the walks of the pieces behind it leave room
-            const int K = ctx->n_pieces;
-            if (!ctx->eval_stream) {
-                CK(cudaStreamCreateWithPriority(&ctx->eval_stream, cudaStreamNonBlocking, ctx->prio_low));
-                CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-                CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-            }
-            for (int i = 0; i < K; ++i) {
-                if (i > 0 && !ctx->piece_stream[i]) CK(cudaStreamCreateWithPriority(&ctx->piece_stream[i], cudaStreamNonBlocking, ctx->prio_high));
-                if (!ctx->ev_piece[i]) CK(cudaEventCreateWithFlags(&ctx->ev_piece[i], cudaEventDisableTiming));
-            }
-            cudaStream_t se = ctx->eval_stream;
-            P.ch.order = order_all;
-            P.pool_slot_base = 0;
-            P.offset_base = 0;
-            P.vol = nullptr;
-            ctx->h_pin[8] = 0;
-            *(int *)&ctx->h_pin[8] = (int)slots;
-            CK(cudaMemcpyAsync(P.pool_cursor, &ctx->h_pin[8], sizeof(int), cudaMemcpyHostToDevice, st));
-            if (ctx->opt_debug_clear_pool) CK(cudaMemsetAsync(ctx->b_pool.p, 0, ctx->b_pool.bytes, st));
-            CK(cudaEventRecord(ctx->ev_fork, st));
-            auto piece_params = [&](int i) {
-                WalkParams Q = P;
-                Q.unit_begin = ctx->piece_unit[i];
-                Q.unit_end = ctx->piece_unit[i + 1];
-                Q.trk_begin = 32 * ctx->piece_blk[i];
-                Q.trk_end = std::min(32 * ctx->piece_blk[i + 1], n);
-                return Q;
-            };
-            for (int i = 0; i < K; ++i) {
-                cudaStream_t sm = i == 0 ? st : ctx->piece_stream[i];
-                if (i > 0) CK(cudaStreamWaitEvent(sm, ctx->ev_fork, 0));
-                const WalkParams Q = piece_params(i);
-                const long long sl = (Q.unit_end - Q.unit_begin) * 32;
-                if (sl > 0) {
-                    k_seed<<<blocks_for(sl, 128), 128, 0, sm>>>(Q);
-                    if (ctx->opt_march)
-                        k_march<<<blocks_for(sl, kMarchThreads), kMarchThreads, 0, sm>>>(Q);
-                    else
-                        k_topo<2><<<blocks_for(sl, kTopoThreads), kTopoThreads, 0, sm>>>(Q);
-                    launches += 2;
-                }
-                CK(cudaEventRecord(ctx->ev_piece[i], sm));
-                if (i == K - 1) cudaEventRecord(ctx->pev[2][1], sm);  // "count": until the last walk is done
-            }
-            ctx->pev_dirty[2] = true;
-            P.opx = ctx->s_px;
-            P.opy = ctx->s_py;
-            P.oqx = ctx->s_qx;
-            P.oqy = ctx->s_qy;
-            P.olen = ctx->s_len;
-            P.oelem = ctx->s_elem;
-            P.vol = want_vol ? ctx->vol_acc : nullptr;
-            for (int i = 0; i < K; ++i) {
-                CK(cudaStreamWaitEvent(se, ctx->ev_piece[i], 0));
-                if (i == K - 1) cudaEventRecord(ctx->pev[4][0], se);  // "fill": what is left to do once the last walk is done
-                const WalkParams Q = piece_params(i);
-                const long long tb = Q.trk_begin, te = Q.trk_end;
-                if (te <= tb) continue;
-                k_fixup_tracks<<<blocks_for(te - tb, 128), 128, 0, se>>>(Q);
-                long long *off = (long long *)ctx->b_offsets.p;
-                CK((exclusive_scan<int, long long>(ctx, (const int *)ctx->b_count.p + tb, off + tb, te - tb, 0LL, se, i > 0 ? off + tb : nullptr)));
-                k_guard<<<1, 1, 0, se>>>(off + te, 0LL, ctx->cap, P.pool_cursor, P.pool_blocks, d_guard(ctx));
-                WalkParams PE = Q;
-                PE.lmin = lmin_eval;
-                PE.cancel = d_guard(ctx);
-                if (PE.ch.order) PE.ch.order = ctx->order_eval;
-                k_eval3<<<blocks_for((PE.unit_end - PE.unit_begin) * 32 * 32, kEval3Threads), kEval3Threads, 0, se>>>(PE);
-                EvalParams E{};
-                E.m = P.m;
-                E.t = ctx->t;
-                E.ang = P.ang;
-                E.offsets = P.offsets;
-                E.n_tracks = n;
-                E.olen = P.olen;
-                E.status = P.status;
-                E.tsum = P.tsum;
-                E.rtol = rtol;
-                E.trk_begin = tb;
-                E.trk_end = te;
-                E.offset_base = 0;
-                E.cancel = PE.cancel;
-                k_track_status<<<blocks_for(te - tb, 128), 128, 0, se>>>(E);
-                launches += 7;
-                CK(cudaGetLastError());
-            }
-            CK(cudaMemcpyAsync(&ctx->h_pin[1], (long long *)ctx->b_offsets.p + n, sizeof(long long), cudaMemcpyDeviceToHost, se));
-            cudaEventRecord(ctx->pev[4][1], se);
-            ctx->pev_dirty[4] = true;
-            ctx->pev_dirty[3] = false;
-            ctx->phase_ms[3] = 0.0;  // (the scans run between the evaluations)
-            CK(cudaEventRecord(ctx->ev_join, se));
-            CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
-            ctx->res_trk_begin = 0;
-            ctx->res_trk_end = n;
-            ctx->res_off_base = 0;
-            ctx->deferred_total = true;
-            *deferred_verify = true;
-            *launches_io += launches;
-            return RT_OK;
-        }
         // ---- seeds, count+record walk, per-track fix-up, offsets of the batch
         P.trk_begin = b;
         P.trk_end = e;
@@ -1093,7 +961,8 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
         launches += 6;
         CK(cudaMemcpyAsync(&ctx->h_pin[1], (long long *)ctx->b_offsets.p + e, sizeof(long long), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&ctx->h_pin[9], P.pool_cursor, sizeof(int), cudaMemcpyDeviceToHost, st));
-        if (optimistic) {
+        if (!multi && !cb && ctx->cap_cfg == 0 && ctx->opt_optimistic && !ctx->skip_optimistic_once && ctx->fit_gen == ctx->trace_gen &&
+            ctx->b_seg_d.p && ctx->cap > 0) {
             // ---- optimistic evaluation: no host round trip between the walk and the evaluation (see rt_ctx::opt_optimistic)
             k_guard<<<1, 1, 0, st>>>((const long long *)ctx->b_offsets.p + e, base, ctx->cap, P.pool_cursor, P.pool_blocks, d_guard(ctx));
             P.opx = ctx->s_px;
@@ -1330,7 +1199,6 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         key.chunk_len = chunk_len;
         key.band = ctx->opt_band_chunks;
         key.order_grid = ctx->opt_order_grid + 1000 * ctx->opt_order_classes;
-        key.pieces = (single && ctx->opt_pieces > 1 && n_blocks >= 64LL * ctx->opt_pieces) ? std::min(ctx->opt_pieces, (int)rt_ctx::kMaxPieces) : 1;
         key.n = n;
         const bool reuse = ctx->opt_plan_cache && key == ctx->plan_key && ctx->n_units > 0;
         ChunkPlan &ch = P.ch;
@@ -1346,25 +1214,8 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
                                                                          (ChunkLayout *)ctx->b_layout.p, (int *)ctx->b_blk_chunks.p);
             CK((exclusive_scan<int, long long>(ctx, (const int *)ctx->b_blk_chunks.p, (long long *)ctx->b_unit_base.p, n_blocks)));
             CK(cudaMemcpyAsync(&ctx->h_pin[0], (long long *)ctx->b_unit_base.p + n_blocks, sizeof(long long), cudaMemcpyDeviceToHost, st));
-            std::vector<long long> h_ub;
-            if (key.pieces > 1) {
-                h_ub.resize((size_t)n_blocks + 1);
-                CK(cudaMemcpyAsync(h_ub.data(), ctx->b_unit_base.p, sizeof(long long) * h_ub.size(), cudaMemcpyDeviceToHost, st));
-            }
             CK(cudaStreamSynchronize(st));
             ctx->n_units = ctx->h_pin[0];
-            ctx->n_pieces = 1;
-            if (key.pieces > 1) {  // pieces of about equal numbers of units, cut at 32-track blocks
-                ctx->n_pieces = key.pieces;
-                ctx->piece_blk[0] = 0;
-                for (int i = 1; i < key.pieces; ++i) {
-                    const long long target = ctx->n_units * i / key.pieces;
-                    long long bq = (long long)(std::lower_bound(h_ub.begin(), h_ub.end(), target) - h_ub.begin());
-                    ctx->piece_blk[i] = std::min(std::max(bq, ctx->piece_blk[i - 1]), n_blocks);
-                }
-                ctx->piece_blk[key.pieces] = n_blocks;
-                for (int i = 0; i <= key.pieces; ++i) ctx->piece_unit[i] = h_ub[(size_t)ctx->piece_blk[i]];
-            }
             launches += 5;
         }
         const long long n_units = ctx->n_units;
@@ -1409,16 +1260,13 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
                 while (gp < G) gp <<= 1;
                 CK(ensure(ctx->b_order, sizeof(int) * (size_t)n_units * (two ? 2 : 1)));
                 CK(ensure(ctx->b_okeys, sizeof(int) * (size_t)n_units));
-                PieceCuts cuts{};
-                cuts.n = ctx->n_pieces;
-                for (int i = 0; i <= ctx->n_pieces; ++i) cuts.blk[i] = (int)ctx->piece_blk[i];
                 for (int pass = 0; pass < (two ? 2 : 1); ++pass) {
                     const int classes = (two && pass == 0 && isfinite(chunk_len)) ? ctx->opt_order_classes : 1;
-                    size_t n_keys = (size_t)gp * gp * classes * ctx->n_pieces;
+                    size_t n_keys = (size_t)gp * gp * classes;
                     CK(ensure(ctx->b_ohist, sizeof(int) * (3 * n_keys + 1)));
                     int *hist = (int *)ctx->b_ohist.p, *ptrs = hist + n_keys, *cursor = ptrs + n_keys + 1;
                     CK(cudaMemsetAsync(hist, 0, sizeof(int) * (3 * n_keys + 1), st));
-                    k_unit_keys<<<blocks_for(n_units, 256), 256, 0, st>>>(P, G, classes, gp * gp, chunk_len, cuts, (int *)ctx->b_okeys.p, hist);
+                    k_unit_keys<<<blocks_for(n_units, 256), 256, 0, st>>>(P, G, classes, gp * gp, chunk_len, (int *)ctx->b_okeys.p, hist);
                     CK((exclusive_scan<int, int>(ctx, hist, ptrs, (long long)n_keys)));
                     k_unit_scatter<<<blocks_for(n_units, 256), 256, 0, st>>>(n_units, (const int *)ctx->b_okeys.p, ptrs, cursor,
                                                                             (int *)ctx->b_order.p + (size_t)pass * n_units);
@@ -2247,8 +2095,6 @@ extern "C" int rt_set_option(rt_ctx *ctx, const char *name, double value) {
         ctx->opt_band_cost = value;
     else if (n == "order_classes" && value >= 0.0 && value <= 64.0)
         ctx->opt_order_classes = (int)value;
-    else if (n == "pieces" && value >= 1.0 && value <= (double)rt_ctx::kMaxPieces)
-        ctx->opt_pieces = (int)value;
     else if (n == "plan_cache")
         ctx->opt_plan_cache = value != 0.0;
     else if (n == "optimistic")

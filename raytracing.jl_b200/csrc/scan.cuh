@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_tile_offsets(Tout *tile_s
 
 template <typename Tin, typename Tout>
 __global__ void __launch_bounds__(kScanThreads) k_scan_apply(const Tin *in, Tout *out, const Tout *tile_offsets,
-                                                             long long n, Tout carry, const Tout *carry_at) {
+                                                             long long n, Tout carry) {
     __shared__ Tout total;
     long long base = blockIdx.x * (long long)kScanTile + threadIdx.x * kScanItems;
     Tout v[kScanItems];
@@ -79,11 +79,10 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(const Tin *in, Tout
         v[q] = (base + q < n) ? (Tout)in[base + q] : Tout(0);
         s += v[q];
     }
-    if (carry_at) carry += *carry_at;  // (a running total left on the device by the scan of the range in front)
     Tout ex = block_excl_scan<Tout>(s, &total) + tile_offsets[blockIdx.x] + carry;
 #pragma unroll
     for (int q = 0; q < kScanItems; ++q) {
-        if (base + q < n && !(carry_at == out && base + q == 0)) out[base + q] = ex;  // (out[0] IS the running total then)
+        if (base + q < n) out[base + q] = ex;
         ex += v[q];
         if (base + q == n - 1) out[n] = ex;
     }

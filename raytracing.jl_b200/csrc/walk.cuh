@@ -196,16 +196,8 @@ __device__ __forceinline__ unsigned morton2(unsigned x, unsigned y) {
     return spread(x) | (spread(y) << 1);
 }
 
-// Pieces: the shard cut into a few uid ranges (whole 32-track blocks) whose walks and evaluations are launched separately, so
-// that the evaluation of the pieces that are done fills the SMs the last walkers leave idle (rt_b200.cu, segmentize_single).
-// The piece is the major sort key: positions [unit_base[blk[i]], unit_base[blk[i + 1]]) of both orders hold piece i's units.
-struct PieceCuts {
-    int n;
-    int blk[9];  // first 32-track block of every piece, blk[n] = number of blocks
-};
-
-__global__ void k_unit_keys(const __grid_constant__ WalkParams P, int G, int classes, int keys_per_class, double chunk_len,
-                            const __grid_constant__ PieceCuts cuts, int *keys, int *hist) {
+__global__ void k_unit_keys(const __grid_constant__ WalkParams P, int G, int classes, int keys_per_class, double chunk_len, int *keys,
+                            int *hist) {
     long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (u >= P.ch.n_units) return;
     int b = P.ch.unit_block[u];
@@ -236,9 +228,6 @@ __global__ void k_unit_keys(const __grid_constant__ WalkParams P, int G, int cla
         bin = min(max(bin, 0), classes - 1);
         key += bin * keys_per_class;
     }
-    int piece = 0;
-    for (int i = 1; i < cuts.n; ++i) piece += (b >= cuts.blk[i]) ? 1 : 0;
-    key += piece * classes * keys_per_class;
     keys[u] = key;
     atomicAdd(&hist[key], 1);
 }
