@@ -514,7 +514,8 @@ def main():
                             and vol_ok and parity["segments_match_unsharded"] is not False)
     else:
         parity["ok"] = bool(parity["ok"] and vol_ok)
-    launches = int(st["launches"] + 1) * args.steps
+    # kernels of one steady-state call (rt_segmentize's own count) + with a communicator the k_normalise rt_volumes launches behind the all-reduce
+    launches = int(st["launches"] + (1 if world > 1 else 0)) * args.steps
     fallbacks = int(tg.info("verify_fallbacks"))
     bad_status = int(tg.bad_status)
 

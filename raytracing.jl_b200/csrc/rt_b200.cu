@@ -170,6 +170,7 @@ struct rt_ctx {
     cudaEvent_t ev_fill_done = nullptr;                     // ctx->stream: the sums are complete
     cudaEvent_t ev_vol_free[2] = {nullptr, nullptr};        // coll_stream: the collective has consumed buffer i (and b_voln is ready)
     bool ev_vol_used[2] = {false, false};
+    bool voln_done = false;                                 // b_voln already holds the normalised volumes of the last rt_segmentize (no communicator)
     int voln_ready = -1;                                    // index of the event that marks b_voln complete (-1: main stream)
 };
 
@@ -215,14 +216,14 @@ static void release(DevBuf &b) {
 static inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 template <typename Tin, typename Tout>
-static cudaError_t exclusive_scan(rt_ctx *ctx, const Tin *in, Tout *out, long long n, Tout carry = Tout(0)) {
+static cudaError_t exclusive_scan(rt_ctx *ctx, const Tin *in, Tout *out, long long n, Tout carry = Tout(0), ScanGuard guard = ScanGuard{}) {
     long long n_tiles = (n + kScanTile - 1) / kScanTile;
     cudaError_t e = ensure(ctx->b_tile, sizeof(Tout) * (size_t)n_tiles);
     if (e != cudaSuccess) return e;
     Tout *tiles = (Tout *)ctx->b_tile.p;
     k_scan_tile_sums<Tin, Tout><<<(unsigned)n_tiles, kScanThreads, 0, ctx->stream>>>(in, tiles, n);
     k_scan_tile_offsets<Tout><<<1, kScanThreads, 0, ctx->stream>>>(tiles, n_tiles);
-    k_scan_apply<Tin, Tout><<<(unsigned)n_tiles, kScanThreads, 0, ctx->stream>>>(in, out, tiles, n, carry);
+    k_scan_apply<Tin, Tout><<<(unsigned)n_tiles, kScanThreads, 0, ctx->stream>>>(in, out, tiles, n, carry, guard);
     return cudaGetLastError();
 }
 
@@ -796,11 +797,6 @@ __global__ void k_normalise(const double *in, double *out, int n, double denom) 
     if (i < n) out[i] = in[i] / denom;  // volumes ./= n_azim_2, src/trackgenerator.jl:386
 }
 
-// optimistic evaluation: does the batch fit the Segment columns and did the record pool hold every record?  (one thread)
-__global__ void k_guard(const long long *total_at, long long base, long long cap, const int *pool_cursor, int pool_blocks, int *cancel) {
-    *cancel = (*total_at - base > cap || *pool_cursor > pool_blocks) ? 1 : 0;
-}
-
 extern "C" int rt_set_segment_capacity(rt_ctx *ctx, int64_t max_segments_resident) {
     if (!ctx || max_segments_resident < 0) return RT_ERR_ARG;
     ctx->cap_cfg = max_segments_resident;
@@ -849,8 +845,7 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
     const size_t nn = (size_t)std::max<long long>(n, 1);
     double launches = 0;
     const int *order_all = P.ch.order;
-    CK(ensure(ctx->b_tsum, sizeof(double) * nn));
-    CK(cudaMemsetAsync(ctx->b_tsum.p, 0, sizeof(double) * nn, st));
+    CK(ensure(ctx->b_tsum, sizeof(double) * nn));  // (cleared per batch by k_seed, like the pool cursor and the volume accumulator)
     CK(ensure(ctx->b_pool_cursor, sizeof(int)));
     P.tsum = (double *)ctx->b_tsum.p;
     P.pool_cursor = (int *)ctx->b_pool_cursor.p;
@@ -942,9 +937,9 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
         P.pool_slot_base = u0 * 32;
         P.vol = nullptr;
         P.offset_base = 0;
-        ctx->h_pin[8] = 0;
-        *(int *)&ctx->h_pin[8] = (int)slots;
-        CK(cudaMemcpyAsync(P.pool_cursor, &ctx->h_pin[8], sizeof(int), cudaMemcpyHostToDevice, st));
+        P.cursor_init = (int)slots;
+        P.zero_vol = (want_vol && B0 == 0) ? ctx->vol_acc : nullptr;  // (+1: the failed-rank flag of rt_volumes)
+        P.zero_vol_n = (long long)P.m.n_cells + 1;
         if (ctx->opt_debug_clear_pool) CK(cudaMemsetAsync(ctx->b_pool.p, 0, ctx->b_pool.bytes, st));
         if (B0 > 0) tic(ctx, 2);  // (the first batch's count phase started with the chunk plan)
         k_seed<<<blocks_for(slots, 128), 128, 0, st>>>(P);
@@ -956,15 +951,18 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
         CK(cudaGetLastError());
         toc(ctx, 2);
         tic(ctx, 3);
-        CK((exclusive_scan<int, long long>(ctx, (const int *)ctx->b_count.p + b, (long long *)ctx->b_offsets.p + b, e - b, base)));
+        const bool optimistic = !multi && !cb && ctx->cap_cfg == 0 && ctx->opt_optimistic && !ctx->skip_optimistic_once &&
+                                ctx->fit_gen == ctx->trace_gen && ctx->b_seg_d.p && ctx->cap > 0;
+        ScanGuard guard{};
+        if (optimistic) guard = ScanGuard{d_guard(ctx), base, ctx->cap, P.pool_cursor, P.pool_blocks};
+        CK((exclusive_scan<int, long long>(ctx, (const int *)ctx->b_count.p + b, (long long *)ctx->b_offsets.p + b, e - b, base, guard)));
         toc(ctx, 3);
         launches += 6;
         CK(cudaMemcpyAsync(&ctx->h_pin[1], (long long *)ctx->b_offsets.p + e, sizeof(long long), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&ctx->h_pin[9], P.pool_cursor, sizeof(int), cudaMemcpyDeviceToHost, st));
-        if (!multi && !cb && ctx->cap_cfg == 0 && ctx->opt_optimistic && !ctx->skip_optimistic_once && ctx->fit_gen == ctx->trace_gen &&
-            ctx->b_seg_d.p && ctx->cap > 0) {
-            // ---- optimistic evaluation: no host round trip between the walk and the evaluation (see rt_ctx::opt_optimistic)
-            k_guard<<<1, 1, 0, st>>>((const long long *)ctx->b_offsets.p + e, base, ctx->cap, P.pool_cursor, P.pool_blocks, d_guard(ctx));
+        if (!optimistic) CK(cudaMemcpyAsync(&ctx->h_pin[9], P.pool_cursor, sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (optimistic) {
+            // ---- optimistic evaluation: no host round trip between the walk and the evaluation (see rt_ctx::opt_optimistic);
+            // the guard (does the batch fit the Segment columns, did the pool hold every record?) is evaluated by the scan
             P.opx = ctx->s_px;
             P.opy = ctx->s_py;
             P.oqx = ctx->s_qx;
@@ -995,8 +993,9 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
             E.trk_end = e;
             E.offset_base = base;
             E.cancel = PE.cancel;
+            E.bad = d_bad(ctx);
             k_track_status<<<blocks_for(e - b, 128), 128, 0, st>>>(E);
-            launches += 3;
+            launches += 2;
             CK(cudaGetLastError());
             toc(ctx, 4);
             // (verification and guard flags come back with the control block at the end of the call, segmentize_once)
@@ -1048,6 +1047,7 @@ static int segmentize_single(rt_ctx *ctx, WalkParams &P, double rtol, bool want_
         E.status = P.status;
         E.tsum = P.tsum;
         E.rtol = rtol;
+        E.bad = d_bad(ctx);
         const bool split = batch_total > cap;
         ctx->fit_gen = (!multi && !split) ? ctx->trace_gen : ~0ULL;  // (the next call with these tracks may skip this round trip)
         if (split) {
@@ -1150,7 +1150,8 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
     const bool want_vol = !(flags & RT_SEG_NO_VOLUMES);
     *verify_failed = false;
     *bad_out = ~0ULL;
-    if (want_vol) CK(cudaMemsetAsync(ctx->vol_acc, 0, sizeof(double) * ((size_t)m.n_cells + 1), st));  // (+1: the failed-rank flag of rt_volumes)
+    // (+1: the failed-rank flag of rt_volumes; the single-walk pipeline clears the accumulator in its first k_seed)
+    if (want_vol && !(mode == 3 && n > 0)) CK(cudaMemsetAsync(ctx->vol_acc, 0, sizeof(double) * ((size_t)m.n_cells + 1), st));
     size_t nn = (size_t)std::max<long long>(n, 1);
     for (int q = 0; q < 8; ++q) ctx->h_pin[kPinCtrlInit + q] = 0;
     ctx->h_pin[kPinCtrlInit + 4] = -1LL;  // "no bad track"
@@ -1444,8 +1445,20 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         }
         toc(ctx, 4);
     }
+    ctx->voln_done = false;
+    if (want_vol && m.n_cells > 0 && ctx->vol_acc && !(ctx->comm && ctx->coll_stream)) {
+        // volumes ./= n_azim_2 right behind the evaluation (rt_volumes would launch it after the host has seen the call return:
+        // one more host round trip with the GPU idle); with a communicator the all-reduce comes first and rt_volumes does both
+        CK(ensure(ctx->b_voln, sizeof(double) * ((size_t)m.n_cells + 1)));
+        tic(ctx, 5);
+        k_normalise<<<blocks_for(m.n_cells, 256), 256, 0, st>>>(ctx->vol_acc, (double *)ctx->b_voln.p, m.n_cells, (double)ctx->n2);
+        CK(cudaGetLastError());
+        toc(ctx, 5);
+        ctx->voln_done = true;
+        launches += 1;
+    }
     unsigned long long bad = ~0ULL;
-    if (n > 0) {
+    if (n > 0 && !single) {  // (the single-walk pipeline's k_track_status reports the failing tracks itself)
         k_first_bad<<<blocks_for(n, 256), 256, 0, st>>>((const int *)ctx->b_status.p, n, d_bad(ctx));
         launches += 1;
     }
@@ -1880,10 +1893,12 @@ extern "C" int rt_volumes(rt_ctx *ctx, double *volumes) {
         if (volumes || !have) CK(cudaStreamSynchronize(cs));
         if (!have) return fail(ctx, RT_ERR_ARG, "rt_volumes: this rank's rt_segmentize failed; it joined the all-reduce with a zero contribution and the failed-rank flag");
     } else {
-        tic(ctx, 5);
-        k_normalise<<<blocks_for(nc, 256), 256, 0, st>>>(src, (double *)ctx->b_voln.p, nc, (double)ctx->n2);
-        CK(cudaGetLastError());
-        toc(ctx, 5);
+        if (!ctx->voln_done) {  // (rt_segmentize normalises right behind the evaluation)
+            tic(ctx, 5);
+            k_normalise<<<blocks_for(nc, 256), 256, 0, st>>>(src, (double *)ctx->b_voln.p, nc, (double)ctx->n2);
+            CK(cudaGetLastError());
+            toc(ctx, 5);
+        }
         ctx->voln_ready = -1;
         if (volumes) CK(cudaStreamSynchronize(st));  // (the copy below runs on the legacy stream, which does not wait for ours)
     }

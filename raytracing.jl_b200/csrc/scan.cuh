@@ -67,9 +67,18 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_tile_offsets(Tout *tile_s
     }
 }
 
+// optimistic evaluation: does the batch fit the Segment columns and did the record pool hold every record?  Checked by the
+// thread that writes the scan's total (the flag is cleared with the control block at the start of the call).
+struct ScanGuard {
+    int *cancel;  // nullptr: no guard
+    long long base, cap;
+    const int *pool_cursor;
+    int pool_blocks;
+};
+
 template <typename Tin, typename Tout>
 __global__ void __launch_bounds__(kScanThreads) k_scan_apply(const Tin *in, Tout *out, const Tout *tile_offsets,
-                                                             long long n, Tout carry) {
+                                                             long long n, Tout carry, const ScanGuard guard) {
     __shared__ Tout total;
     long long base = blockIdx.x * (long long)kScanTile + threadIdx.x * kScanItems;
     Tout v[kScanItems];
@@ -84,7 +93,10 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(const Tin *in, Tout
     for (int q = 0; q < kScanItems; ++q) {
         if (base + q < n) out[base + q] = ex;
         ex += v[q];
-        if (base + q == n - 1) out[n] = ex;
+        if (base + q == n - 1) {
+            out[n] = ex;
+            if (guard.cancel && ((long long)ex - guard.base > guard.cap || *guard.pool_cursor > guard.pool_blocks)) *guard.cancel = 1;
+        }
     }
 }
 

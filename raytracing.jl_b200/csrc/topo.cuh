@@ -325,6 +325,7 @@ struct EvalParams {
     double *tsum;  // per track: sum of segment lengths (atomics)
     double rtol;
     const int *cancel;  // optimistic evaluation cancelled (k_guard): nothing to check
+    unsigned long long *bad;  // min over the failing tracks of (track << 4 | status), or nullptr
 };
 
 // isapprox(track.l, sum(l.(segments)); rtol)  src/track.jl:171-175.  The atomically accumulated sum differs from the
@@ -334,7 +335,11 @@ __global__ void k_track_status(const __grid_constant__ EvalParams P) {
     long long t = P.trk_begin + blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= P.trk_end) return;
     if (P.cancel && *P.cancel) return;
-    if (P.status[t] != 0) return;
+    const int st0 = P.status[t];
+    if (st0 != 0) {  // (failed in the walk)
+        if (P.bad) atomicMin(P.bad, ((unsigned long long)t << 4) | (unsigned long long)(st0 & 15));
+        return;
+    }
     const double len = P.t.len[t];
     double sum = P.tsum[t];
     const double tol = P.rtol * fmax(fabs(len), fabs(sum));
@@ -344,7 +349,10 @@ __global__ void k_track_status(const __grid_constant__ EvalParams P) {
         sum = 0.0;
         for (long long s = b; s < e; ++s) sum += P.olen[s];
     }
-    if (!isapprox(len, sum, 0.0, P.rtol)) P.status[t] = 2;
+    if (!isapprox(len, sum, 0.0, P.rtol)) {
+        P.status[t] = 2;
+        if (P.bad) atomicMin(P.bad, ((unsigned long long)t << 4) | 2ull);
+    }
 }
 
 }  // namespace rt

@@ -80,6 +80,10 @@ struct WalkParams {
     int *pool_cursor;              // next unclaimed block
     int pool_blocks;
     long long pool_slot_base;      // chunk slot (unit*32 + lane) whose first block is block 0
+    // start-of-batch initialisations folded into k_seed (each used to be a memset / copy in front of the first kernel)
+    int cursor_init;               // first unclaimed block = chunk slots of the batch
+    double *zero_vol;              // volume accumulator to clear (first batch of a call), or nullptr
+    long long zero_vol_n;
 };
 
 constexpr int kRecBlock = 256;  // records per pool block (a multiple of 32): with the default chunks of ~128 segments a walker
@@ -260,6 +264,14 @@ __device__ __forceinline__ double bbox_dist(const DevMesh &m, double x, double y
 __global__ void __launch_bounds__(128) k_seed(const __grid_constant__ WalkParams P) {
     long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
+    if (P.pool_cursor) {  // single-walk pipeline: clear what the walk and the evaluation of this batch accumulate into
+        const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x, gsz = gridDim.x * (long long)blockDim.x;
+        if (gtid == 0) *P.pool_cursor = P.cursor_init;
+        if (P.tsum)
+            for (long long i = P.trk_begin + gtid; i < P.trk_end; i += gsz) P.tsum[i] = 0.0;
+        if (P.zero_vol)
+            for (long long i = gtid; i < P.zero_vol_n; i += gsz) P.zero_vol[i] = 0.0;
+    }
     long long slot = P.unit_begin + gw;
     if (slot >= P.unit_end) return;
     long long unit = P.ch.order ? P.ch.order[slot] : slot;
