@@ -32,6 +32,11 @@ constexpr int kEval3Threads = RT_EVAL3_THREADS;
 #ifndef RT_EVAL3_MIN_BLOCKS
 #define RT_EVAL3_MIN_BLOCKS 32
 #endif
+#ifndef RT_EVAL3_PF_AHEAD
+#define RT_EVAL3_PF_AHEAD 64  // L2 prefetch distance in units (= 32 warps each); 0: off
+#endif
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // intersection(track, L) (src/intersection.jl:127-138) through the shared-reciprocal division; `redo` is set when a quotient did
 // not pass ptxas' own acceptance test (zero or extreme numerators): the caller then repeats the formula with the plain operators
@@ -62,6 +67,26 @@ __global__ void __launch_bounds__(kEval3Threads, RT_EVAL3_MIN_BLOCKS) k_eval3(co
     // Everything that only needs the chunk slot is requested at once, BEFORE the early exits (a warp lives for ~4 iterations,
     // so a chain of dependent header loads in front of them costs as much as the arithmetic): count, first records, prefix,
     // seed point next to the unit's block; then the track's data; then the per-angle data.
+#if RT_EVAL3_PF_AHEAD > 0
+    // The records and the slot data of the chunk that the warp RT_EVAL3_PF_AHEAD units behind this one will evaluate are pulled
+    // into L2 now.  They are read exactly once, from DRAM, at the head of that warp's dependent load chain, and under the
+    // evaluation's own 2.2 GB write stream a cold DRAM read costs several times its idle latency (the same kernel storing into an
+    // L2-resident dummy region runs in 0.73 ms instead of 0.96).  Distances of 32 .. 128 units measure the same (-3.3 %), 512 and
+    // more are evicted again before they are used (profiles/r2_eval_ablation.txt).
+    {
+        const long long slot_a = slot + RT_EVAL3_PF_AHEAD;
+        if (slot_a < P.unit_end) {
+            const long long unit_a = P.ch.order ? P.ch.order[slot_a] : slot_a;
+            const long long cidx_a = unit_a * 32 + ls;
+            const char *recs = (const char *)(P.pool + (cidx_a - P.pool_slot_base) * kRecBlock);
+            if (lane < 4) prefetch_l2(recs + 128 * lane);
+            else if (lane == 4) prefetch_l2(P.ch.count + cidx_a);
+            else if (lane == 5) prefetch_l2(P.ch.prefix + cidx_a);
+            else if (lane == 6) prefetch_l2(P.ch.seed_qx + cidx_a);
+            else if (lane == 7) prefetch_l2(P.ch.seed_qy + cidx_a);
+        }
+    }
+#endif
     const long long cidx = unit * 32 + ls;
     const int pb0 = (int)(cidx - P.pool_slot_base);
     int pb = pb0;
@@ -82,7 +107,7 @@ __global__ void __launch_bounds__(kEval3Threads, RT_EVAL3_MIN_BLOCKS) k_eval3(co
     if (cnt <= 0) return;
     int rec = lane < cnt ? rec_first : 1;
 
-    const unsigned long long pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
+    const unsigned long long pol_keep = l2_policy_keep();
     const bool right = P.ang.phi[az] < kPi / 2;  // isless(phi, pi/2), src/intersection.jl:153
     const double delta = P.vol ? P.ang.delta_eff[az] : 0.0;
     const long long base = off_t - P.offset_base + prefix;
@@ -136,12 +161,13 @@ __global__ void __launch_bounds__(kEval3Threads, RT_EVAL3_MIN_BLOCKS) k_eval3(co
             const double dx = p.x - q.x, dy = p.y - q.y;
             const double l = sqrt(dx * dx + dy * dy);  // Segment(p, q): norm(p - q), src/segment.jl:32
             const long long so = base + v;
-            stg_f64_pol(P.opx + so, p.x, pol_stream);
-            stg_f64_pol(P.opy + so, p.y, pol_stream);
-            stg_f64_pol(P.oqx + so, q.x, pol_stream);
-            stg_f64_pol(P.oqy + so, q.y, pol_stream);
-            stg_f64_pol(P.olen + so, l, pol_stream);
-            stg_i32_pol(P.oelem + so, (int)cell + 1, pol_stream);
+            // (plain stores: an evict-first policy or st.cs on the output stream measures 1 % slower, write-through the same)
+            P.opx[so] = p.x;
+            P.opy[so] = p.y;
+            P.oqx[so] = q.x;
+            P.oqy[so] = q.y;
+            P.olen[so] = l;
+            P.oelem[so] = (int)cell + 1;
             if (P.vol) atomicAdd(&P.vol[cell], delta * l);  // volumes[i] += delta_s[a]*l, src/trackgenerator.jl:382
             lsum += l;
             // the geometric conditions of the sequential fast path (walk.cuh); k_march's filters make them hold:
