@@ -225,8 +225,9 @@ int rt_comm_init(rt_ctx *ctx, int32_t n_ranks, int32_t rank, const char id[128])
  * nearest-node queries, knn queries, count-pass ms, fill-pass ms, scan+volumes ms. */
 int rt_stats(rt_ctx *ctx, double stats[8]);
 /* named scalars: "verify_fallbacks", "n_units", "segment_capacity", "count_batches"
- * (uid batches of the single-walk pipeline's count walk) of the last rt_segmentize; "tau_ms" (k_tau alone) of the last
- * rt_optical_lengths */
+ * (uid batches of the single-walk pipeline's count walk) of the last rt_segmentize; "optimistic_cancels" (calls of this context
+ * whose evaluation, launched behind the walk without reading the segment total back, was cancelled by the device-side guard and
+ * repeated); "rho", "band_cost" (shard planning); "tau_ms" (k_tau alone) of the last rt_optical_lengths */
 int rt_info(rt_ctx *ctx, const char *key, double *value);
 /* CUDA-event time (ms) of the last call's device work, by phase: 0 upload+prep, 1 trace, 2 count,
  * 3 scan, 4 fill, 5 volumes(+allreduce) */

@@ -120,6 +120,7 @@ struct rt_ctx {
     // final read-back of the call and repeats the call on the careful path.
     int opt_optimistic = 1;
     bool skip_optimistic_once = false;
+    int optimistic_cancels = 0;        // calls whose optimistic evaluation the device-side guard cancelled (info)
     unsigned long long fit_gen = ~0ULL;  // trace generation whose previous call fitted the Segment columns and the pool in ONE batch
     bool deferred_total = false;
     bool redo_careful = false;         // the repeat asked for by the optimistic path (not a failed verification)
@@ -1469,6 +1470,7 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         ctx->deferred_total = false;
         if (flag_guard) {  // cancelled on the device (Segment columns or record pool too small): repeat on the careful path
             ctx->skip_optimistic_once = true;
+            ctx->optimistic_cancels += 1;
             ctx->fit_gen = ~0ULL;
             ctx->redo_careful = true;
             *verify_failed = true;
@@ -1998,6 +2000,8 @@ extern "C" int rt_info(rt_ctx *ctx, const char *key, double *value) {
         *value = ctx->opt_band_cost;
     else if (k == "count_batches")
         *value = (double)ctx->count_batches;
+    else if (k == "optimistic_cancels")
+        *value = (double)ctx->optimistic_cancels;
     else
         return fail(ctx, RT_ERR_ARG, "rt_info: unknown key %s", key);
     return RT_OK;

@@ -249,6 +249,28 @@ def test_idempotent_and_max_iter(pincell_model):
         assert np.array_equal(tg.segments["element"][off[u]:off[u + 1]], a["element"][a_off[u]:a_off[u] + n_u])
 
 
+def test_optimistic_evaluation_cancelled_on_the_device_is_repeated():
+    """The steady-state call launches the evaluation behind the walk without reading the segment total back (DESIGN.md section 6);
+    the scan's guard cancels it on the device when the batch does not fit the Segment columns of the previous call, and the call
+    is repeated on the careful path: same bits as the oracle, one cancellation counted."""
+    mesh = rt.Mesh(rt.synth.jittered_triangle_mesh(60, 60, seed=5))
+    otg = OracleTrackGenerator(OracleMesh.from_mesh(mesh), 16, 0.01).trace().segmentize(check=False, nthreads=8)
+    tg = rt.TrackGenerator(mesh, 16, 0.01)
+    rt.trace_(tg)
+    rt.segmentize_(tg, max_iter=3, check=False)  # first call after trace!: careful path, Segment columns sized for 3 segments per track
+    small = tg.n_segments
+    rt.segmentize_(tg, max_iter=3, check=False)  # optimistic, fits
+    assert tg.n_segments == small and tg.info("optimistic_cancels") == 0
+    rt.segmentize_(tg, check=False)  # ~20x the segments: does not fit
+    assert tg.info("optimistic_cancels") == 1 and tg.n_segments > 5 * small and tg.info("verify_fallbacks") == 0
+    assert_segments_equal(otg, tg)
+    assert_volumes_close(otg, tg)
+    rt.segmentize_(tg, check=False)  # the careful call re-fitted the columns: optimistic again, and it fits
+    assert tg.info("optimistic_cancels") == 1
+    assert_segments_equal(otg, tg)
+    assert_volumes_close(otg, tg)
+
+
 def test_error_paths(pincell_model):
     tg = rt.TrackGenerator(pincell_model, 8, 0.05)
     with pytest.raises(RuntimeError):
