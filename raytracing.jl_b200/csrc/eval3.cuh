@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kEval3Threads, RT_EVAL3_MIN_BLOCKS) k_eval3(co
     const long long w = blockIdx.x * (long long)(kEval3Threads / 32) + (threadIdx.x >> 5);
     const long long slot = P.unit_begin + (w >> 5);
     if (slot >= P.unit_end) return;
-    if (P.cancel && *P.cancel) return;  // (optimistic launch behind the walk: the batch turned out not to fit, k_guard)
+    if (P.cancel && *P.cancel) return;  // (optimistic launch behind the walk: the batch turned out not to fit, scan.cuh ScanGuard)
     const int ls = (int)(w & 31);
     const long long unit = P.ch.order ? P.ch.order[slot] : slot;
     // Everything that only needs the chunk slot is requested at once, BEFORE the early exits (a warp lives for ~4 iterations,

@@ -324,7 +324,7 @@ struct EvalParams {
     int *status;   // per track
     double *tsum;  // per track: sum of segment lengths (atomics)
     double rtol;
-    const int *cancel;  // optimistic evaluation cancelled (k_guard): nothing to check
+    const int *cancel;  // optimistic evaluation cancelled (scan.cuh ScanGuard): nothing to check
     unsigned long long *bad;  // min over the failing tracks of (track << 4 | status), or nullptr
 };
 

@@ -72,7 +72,7 @@ struct WalkParams {
     double *vol;                   // unnormalised sum(delta_eff*len) per element, or nullptr
     unsigned long long *counters;  // [fast transitions, literal iterations, nn queries, knn queries] or nullptr
     int *verify_fail;
-    const int *cancel;             // optimistic evaluation: set by k_guard when the batch does not fit (nullptr: not used)
+    const int *cancel;             // optimistic evaluation: set by the scan (ScanGuard) when the batch does not fit (nullptr: not used)
     double *tsum;                  // self-verifying pipelines: per-track sum of segment lengths
     // single-walk pipeline (k_topo<2> + k_eval3): pool of record blocks
     int *pool;                     // pool_blocks * kRecBlock records
