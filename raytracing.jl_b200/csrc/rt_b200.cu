@@ -115,9 +115,9 @@ struct rt_ctx {
     double opt_band_cost = 28.0;       // shard planning: cost of one boundary-band cell in fast transitions (measured: cfg4 on 8 GPUs)
     int opt_plan_cache = 1;            // 0: rebuild the chunk plan in every call (test knob)
     // Optimistic evaluation: when the previous call's Segment columns are still allocated, the evaluation is launched right behind
-    // the walk WITHOUT reading the segment total back first; a one-thread guard kernel compares the total (and the record pool's
-    // cursor) with the capacities on the device and cancels the evaluation if they do not fit -- the host learns it with the
-    // final read-back of the call and repeats the call on the careful path.
+    // the walk WITHOUT reading the segment total back first; the thread of the scan that writes the total compares it (and the
+    // record pool's cursor) with the capacities on the device (scan.cuh ScanGuard) and cancels the evaluation if they do not fit --
+    // the host learns it with the final read-back of the call and repeats the call on the careful path.
     int opt_optimistic = 1;
     bool skip_optimistic_once = false;
     int optimistic_cancels = 0;        // calls whose optimistic evaluation the device-side guard cancelled (info)
