@@ -105,7 +105,9 @@ __global__ void __launch_bounds__(kEval3Threads, RT_EVAL3_MIN_BLOCKS) k_eval3(co
     const int j = (int)(unit - ubase);
     if (j >= nch) return;  // (count is only defined for the chunks the track has)
     if (cnt <= 0) return;
-    int rec = lane < cnt ? rec_first : 1;
+    int rec_cur = lane < cnt ? rec_first : 1;  // aligned record vector of this iteration (records 32 i .. 32 i + 31)
+    int rec_prev = 1;                          // ... of the iteration before
+    int rec;
 
     const unsigned long long pol_keep = l2_policy_keep();
     const bool right = P.ang.phi[az] < kPi / 2;  // isless(phi, pi/2), src/intersection.jl:153
@@ -119,16 +121,26 @@ __global__ void __launch_bounds__(kEval3Threads, RT_EVAL3_MIN_BLOCKS) k_eval3(co
     bool bad = false, any_lit = false;
     const int rot = (lane + 31) & 31;
 
-    for (int i0 = 0; i0 < cnt; i0 += 32) {
-        const int v = i0 + lane;
-        // the next iteration's records are requested before this iteration's arithmetic
+    // The lanes are shifted by sh = (first output position) mod 16 so that every warp store starts on a 128-byte line: lane l of
+    // iteration i evaluates segment v = 32 i + l - sh.  A warp store of 32 x 8 bytes then touches 2 lines and 8 sectors instead
+    // of 3 and 9, and the SM -> L2 path, which the six column streams keep busy for 0.35 of the kernel's 0.9 ms, charges a
+    // request per line and a beat per sector.  The records stay loaded in aligned vectors (one 128-byte line each) and are
+    // rotated into place with two shuffles.
+    const int sh = (int)(base & 15);
+    const int src_lane = (lane - sh) & 31;
+    for (int i0 = 0; i0 < cnt + sh; i0 += 32) {
+        const int v = i0 + lane - sh;
         int rec_next = 1;
         {
             const int i1 = i0 + 32;
             if (i1 < cnt && (i1 & (kRecBlock - 1)) == 0) pb = P.pool_next[pb];
             if (i1 + lane < cnt) rec_next = P.pool[(long long)pb * kRecBlock + ((i1 + lane) & (kRecBlock - 1))];
         }
-        const bool fast = (rec & 1) == 0;  // (lanes beyond the chunk's end carry rec = 1)
+        {
+            const int a = __shfl_sync(FULL, rec_prev, src_lane), b = __shfl_sync(FULL, rec_cur, src_lane);
+            rec = lane < sh ? a : b;
+        }
+        const bool fast = (rec & 1) == 0;  // (lanes outside the chunk carry rec = 1)
         const unsigned h = (unsigned)rec >> 2;
         const unsigned cell = fast ? h / 3u : h;
         const unsigned kin = h - 3u * cell;
@@ -147,8 +159,9 @@ __global__ void __launch_bounds__(kEval3Threads, RT_EVAL3_MIN_BLOCKS) k_eval3(co
         // hand-over of the exit points: lane i-1's q is my p; lane 0 takes the previous iteration's lane 31
         const double rx = __shfl_sync(FULL, q.x, rot), ry = __shfl_sync(FULL, q.y, rot);
         const int rfast = __shfl_sync(FULL, (int)fast, rot);
-        P2 p{lane ? rx : cqx, lane ? ry : cqy};
-        const bool have = (lane ? rfast : cfast) != 0;
+        const bool from_left = lane != 0 && v != 0;  // (the chunk's first segment takes the seed point, wherever its lane is)
+        P2 p{from_left ? rx : cqx, from_left ? ry : cqy};
+        const bool have = (from_left ? rfast : cfast) != 0;
         cqx = rx;
         cqy = ry;
         cfast = rfast;
@@ -176,10 +189,11 @@ __global__ void __launch_bounds__(kEval3Threads, RT_EVAL3_MIN_BLOCKS) k_eval3(co
             const bool lt = right ? (p.x < q.x) : (p.x > q.x);
             const bool in_first = lt || (p.x == q.x && !kin_lt_kout);
             bad = bad || par || !in_first || !(l > P.lmin);
-        } else if (v < cnt) {
+        } else if ((unsigned)v < (unsigned)cnt) {
             any_lit = true;
         }
-        rec = rec_next;
+        rec_prev = rec_cur;
+        rec_cur = rec_next;
     }
     if (bad) atomicExch(P.verify_fail, 1);
 
