@@ -248,16 +248,31 @@ def strong_block(name, rank, world, local, dist, torch, steps=3):
     bcs = rt.BoundaryConditions(top=rt.Reflective, bottom=rt.Reflective, right=rt.Reflective, left=rt.Reflective)
     area = rt.synth.mesh_area(model)
 
+    retimed = []
+
     def timed(tg, k):
         rt.segmentize_(tg, rtol=RTOL, check=False, fetch_volumes=False)  # warm-up (allocations, first-touch)
-        dist.barrier()
-        torch.cuda.synchronize()
-        tg.timer_start()
-        ph = []
-        for _ in range(k):
-            rt.segmentize_(tg, rtol=RTOL, check=False, fetch_volumes=False)
-            ph.append(tg.phase_ms())
-        ms = tg.timer_stop() / k
+        for attempt in range(2):
+            dist.barrier()
+            torch.cuda.synchronize()
+            tg.timer_start()
+            ph, wall = [], []
+            for _ in range(k):
+                t0 = time.perf_counter()
+                rt.segmentize_(tg, rtol=RTOL, check=False, fetch_volumes=False)
+                wall.append(round((time.perf_counter() - t0) * 1e3, 2))
+                ph.append(tg.phase_ms())
+            ms = tg.timer_stop() / k
+            print(f"[rank {rank}] {name} {'sharded' if tg.uid_end - tg.uid_begin < tg.n_total_tracks else 'unsharded'}: host wall per call (ms) {wall}",
+                  file=sys.stderr)
+            # k is small (the calls take 0.02 .. 1 s): one call disturbed on the host side (observed once: +60 ms in one of three
+            # calls on a fresh box) would decide the figure, so a region whose slowest call is far off its fastest is measured again, once
+            off = torch.tensor([1.0 if max(wall) > 1.15 * min(wall) + 1.0 else 0.0], dtype=torch.float64, device="cuda")
+            dist.all_reduce(off, op=dist.ReduceOp.MAX)
+            if attempt == 0 and off.item() > 0:
+                retimed.append(name)
+                continue
+            break
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         mine = torch.tensor([float(np.mean([p[k] for p in ph])) for k in ("count", "fill", "volumes")] + [ms, tg.info("count_batches")],
@@ -289,6 +304,7 @@ def strong_block(name, rank, world, local, dist, torch, steps=3):
                 "per_rank_ms[walk, evaluation, volumes, step, walk_batches]": walks,
                 "walk_spread": (max(w[0] for w in walks) - min(w[0] for w in walks)) / max(float(np.mean([w[0] for w in walks])), 1e-9),
                 "volumes_sum_over_area": float(tg.volumes.sum() / area)})
+    out["retimed"] = bool(retimed)
     if one is not None:
         out["efficiency_vs_n1"] = one / (world * ms)
         out["segments_match_unsharded"] = bool(nseg == out["segments"])
