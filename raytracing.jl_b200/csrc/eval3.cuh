@@ -32,6 +32,9 @@ constexpr int kEval3Threads = RT_EVAL3_THREADS;
 #ifndef RT_EVAL3_MIN_BLOCKS
 #define RT_EVAL3_MIN_BLOCKS 32
 #endif
+#ifndef RT_EVAL3_ALIGN
+#define RT_EVAL3_ALIGN 16  // the first lane's output position is a multiple of this many segments (16 doubles = one 128-byte line)
+#endif
 #ifndef RT_EVAL3_PF_AHEAD
 #define RT_EVAL3_PF_AHEAD 64  // L2 prefetch distance in units (= 32 warps each); 0: off
 #endif
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(kEval3Threads, RT_EVAL3_MIN_BLOCKS) k_eval3(co
     // of 3 and 9, and the SM -> L2 path, which the six column streams keep busy for 0.35 of the kernel's 0.9 ms, charges a
     // request per line and a beat per sector.  The records stay loaded in aligned vectors (one 128-byte line each) and are
     // rotated into place with two shuffles.
-    const int sh = (int)(base & 15);
+    const int sh = (int)(base & (RT_EVAL3_ALIGN - 1));
     const int src_lane = (lane - sh) & 31;
     for (int i0 = 0; i0 < cnt + sh; i0 += 32) {
         const int v = i0 + lane - sh;
@@ -173,8 +176,8 @@ __global__ void __launch_bounds__(kEval3Threads, RT_EVAL3_MIN_BLOCKS) k_eval3(co
         if (fast) {
             const double dx = p.x - q.x, dy = p.y - q.y;
             const double l = sqrt(dx * dx + dy * dy);  // Segment(p, q): norm(p - q), src/segment.jl:32
-            const long long so = base + v;
             // (plain stores: an evict-first policy or st.cs on the output stream measures 1 % slower, write-through the same)
+            const long long so = base + v;
             P.opx[so] = p.x;
             P.opy[so] = p.y;
             P.oqx[so] = q.x;

@@ -106,8 +106,10 @@ struct rt_ctx {
         unsigned long long gen = ~0ULL;
         double chunk_len = -1.0;
         int band = -1, order_grid = -1;
+        double band_min = -1.0, band_div = -1.0;
         long long n = -1;
-        bool operator==(const PlanKey &o) const { return gen == o.gen && chunk_len == o.chunk_len && band == o.band && order_grid == o.order_grid && n == o.n; }
+        bool operator==(const PlanKey &o) const { return gen == o.gen && chunk_len == o.chunk_len && band == o.band && order_grid == o.order_grid && n == o.n &&
+                   band_min == o.band_min && band_div == o.band_div; }
     } plan_key;
     bool plan_has_order = false;
     int opt_debug_clear_pool = 0;      // test hook (initcheck): zero the record pool before every walk, so that the evaluation's speculative
@@ -125,7 +127,14 @@ struct rt_ctx {
     bool deferred_total = false;
     bool redo_careful = false;         // the repeat asked for by the optimistic path (not a failed verification)
 
-    int opt_band_chunks = 1;           // 8x shorter chunks for tracks that run along the bounding box (walk.cuh k_plan_chunks)
+    int opt_band_chunks = 1;           // shorter chunks for tracks that run along the bounding box (walk.cuh k_plan_chunks)
+    // ... when that stretch is longer than opt_band_min regular chunks, into chunks opt_band_div times shorter.  Both are relative to
+    // the regular chunk: where tracks are plentiful (cfg4, cfg5: a chunk is a whole track) fine chunks would only multiply the
+    // chunk slots.  0.0625 x 192 = 12 crossings: on cfg3 the two angles next to each axis qualify; with the 0.25 of round 1 the
+    // second one did not below 128-segment chunks and its band stretches were the walk's longest serial chains
+    // (profiles/r2_chunk_band.txt: walk phase 0.70 -> 0.62 ms)
+    double opt_band_min = 0.0625;
+    double opt_band_div = 8.0;
     int opt_march = 1;                 // single-walk pipeline: k_march (register-resident loop) instead of k_topo<2>
     long long opt_pool_slots = 0;      // test hook: at most this many chunk slots per count batch (0: as many as fit)
     double opt_pool_extra = 1.25;      // spare pool blocks, as a multiple of (expected segments / kRecBlock)
@@ -142,7 +151,7 @@ struct rt_ctx {
                                        // only.  Three bins: finer ones cost more in locality than they gain in balance (profiles/r2_walk_order.txt)
     int n_sm = 148;
     long long n_units = 0;
-    double opt_chunk_segments = 128.0;              // minimum expected segments per chunk
+    double opt_chunk_segments = 192.0;              // minimum expected segments per chunk (profiles/r2_chunk_band.txt)
     double opt_target_walkers = 148.0 * 2048.0 * 4.0;  // chunks are sized so that about this many walkers exist
     double sum_len = 0.0;              // total track length of the shard
     double edge_sum = 0.0, area = 0.0;  // mesh density scalars (chunk sizing)
@@ -1200,6 +1209,8 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
         key.gen = ctx->trace_gen;
         key.chunk_len = chunk_len;
         key.band = ctx->opt_band_chunks;
+        key.band_min = ctx->opt_band_min;
+        key.band_div = ctx->opt_band_div;
         key.order_grid = ctx->opt_order_grid + 1000 * ctx->opt_order_classes;
         key.n = n;
         const bool reuse = ctx->opt_plan_cache && key == ctx->plan_key && ctx->n_units > 0;
@@ -1210,7 +1221,7 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
             CK(ensure(ctx->b_blk_chunks, sizeof(int) * (size_t)n_blocks));
             CK(ensure(ctx->b_unit_base, sizeof(long long) * ((size_t)n_blocks + 1)));
             PlanGeom pg{ctx->t.px, ctx->t.py, ctx->t.qx, ctx->t.qy, {m.bbmin[0], m.bbmin[1]}, {m.bbmax[0], m.bbmax[1]},
-                        ctx->opt_band_chunks ? ctx->lmax : 0.0};
+                        ctx->opt_band_chunks ? ctx->lmax : 0.0, ctx->opt_band_min * chunk_len, chunk_len / ctx->opt_band_div};
             CK(ensure(ctx->b_layout, sizeof(ChunkLayout) * (size_t)n));
             k_plan_chunks<<<blocks_for(n_blocks * 32, 128), 128, 0, st>>>(n, ctx->t.len, chunk_len, pg, (int *)ctx->b_nch.p,
                                                                          (ChunkLayout *)ctx->b_layout.p, (int *)ctx->b_blk_chunks.p);
@@ -1268,7 +1279,7 @@ static int segmentize_once(rt_ctx *ctx, double tiny_step, int32_t k, double rtol
                     CK(ensure(ctx->b_ohist, sizeof(int) * (3 * n_keys + 1)));
                     int *hist = (int *)ctx->b_ohist.p, *ptrs = hist + n_keys, *cursor = ptrs + n_keys + 1;
                     CK(cudaMemsetAsync(hist, 0, sizeof(int) * (3 * n_keys + 1), st));
-                    k_unit_keys<<<blocks_for(n_units, 256), 256, 0, st>>>(P, G, classes, gp * gp, chunk_len, (int *)ctx->b_okeys.p, hist);
+                    k_unit_keys<<<blocks_for(n_units, 256), 256, 0, st>>>(P, G, classes, gp * gp, chunk_len, chunk_len / ctx->opt_band_div, (int *)ctx->b_okeys.p, hist);
                     CK((exclusive_scan<int, int>(ctx, hist, ptrs, (long long)n_keys)));
                     k_unit_scatter<<<blocks_for(n_units, 256), 256, 0, st>>>(n_units, (const int *)ctx->b_okeys.p, ptrs, cursor,
                                                                             (int *)ctx->b_order.p + (size_t)pass * n_units);
@@ -2120,6 +2131,10 @@ extern "C" int rt_set_option(rt_ctx *ctx, const char *name, double value) {
         ctx->opt_optimistic = value != 0.0;
     else if (n == "band_chunks")
         ctx->opt_band_chunks = value != 0.0;
+    else if (n == "band_min" && value >= 0.0)
+        ctx->opt_band_min = value;
+    else if (n == "band_div" && value >= 1.0 && value <= 64.0)
+        ctx->opt_band_div = value;
     else if (n == "pool_slots" && value >= 0.0)
         ctx->opt_pool_slots = (long long)value;
     else if (n == "pool_extra" && value >= 0.0)

@@ -113,6 +113,8 @@ struct PlanGeom {
     const double *px, *py, *qx, *qy;
     double bbmin[2], bbmax[2];
     double band;  // width of the boundary band that counts (the longest mesh edge); 0: uniform chunks only
+    double band_min;  // a head / tail gets chunks of its own when it is longer than this
+    double band_len;  // ... of this length (both derived from the regular chunk length, see rt_ctx::opt_band_min)
 };
 
 // length of the initial part of a track of length `len` whose coordinate a(s) = a0 + s * (a1 - a0) / len stays within `band` of lo / hi
@@ -148,17 +150,17 @@ __global__ void k_plan_chunks(long long n_tracks, const double *len, double chun
                         prefix_in_band(l, G.py[t], G.qy[t], G.bbmin[1], G.bbmax[1], G.band));
             tail = fmax(prefix_in_band(l, G.qx[t], G.px[t], G.bbmin[0], G.bbmax[0], G.band),
                         prefix_in_band(l, G.qy[t], G.py[t], G.bbmin[1], G.bbmax[1], G.band));
-            if (!(head > 0.25 * chunk_len)) head = 0.0;  // an ordinary end: a few band cells, not worth chunks of its own
-            if (!(tail > 0.25 * chunk_len)) tail = 0.0;
+            if (!(head > G.band_min)) head = 0.0;  // an ordinary end: a few band cells, not worth chunks of its own
+            if (!(tail > G.band_min)) tail = 0.0;
         }
         if (head == 0.0 && tail == 0.0) {
             n = count(ceil(l / chunk_len));
             L.n_mid = n;
         } else if (head + tail >= l) {  // the whole track runs along the boundary
-            n = count(ceil(l / (chunk_len / 8.0)));
+            n = count(ceil(l / G.band_len));
             L.n_mid = n;
         } else {
-            const int nh = head > 0.0 ? count(ceil(head / (chunk_len / 8.0))) : 0, nt = tail > 0.0 ? count(ceil(tail / (chunk_len / 8.0))) : 0;
+            const int nh = head > 0.0 ? count(ceil(head / G.band_len)) : 0, nt = tail > 0.0 ? count(ceil(tail / G.band_len)) : 0;
             const int nm = count(ceil((l - head - tail) / chunk_len));
             if (nh + nm + nt <= kMaxChunksPerTrack) {
                 n = nh + nm + nt;
@@ -200,8 +202,8 @@ __device__ __forceinline__ unsigned morton2(unsigned x, unsigned y) {
     return spread(x) | (spread(y) << 1);
 }
 
-__global__ void k_unit_keys(const __grid_constant__ WalkParams P, int G, int classes, int keys_per_class, double chunk_len, int *keys,
-                            int *hist) {
+__global__ void k_unit_keys(const __grid_constant__ WalkParams P, int G, int classes, int keys_per_class, double chunk_len, double band_len,
+                            int *keys, int *hist) {
     long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (u >= P.ch.n_units) return;
     int b = P.ch.unit_block[u];
@@ -226,7 +228,7 @@ __global__ void k_unit_keys(const __grid_constant__ WalkParams P, int G, int cla
         const int n_head = L.n_head, n_mid = L.n_mid;
         const bool band = !(n_head == 0 && n_mid == n) && (jj < n_head || jj >= n_head + n_mid);
         const double len_j = chunk_start(L, P.t.len[t], n, jj + 1) - chunk_start(L, P.t.len[t], n, jj);
-        double d = (band ? 8.0 : 1.0) * len_j / chunk_len + (j == 0 ? 1.0 : 0.0) + (jj == n - 1 ? 0.25 : 0.0);
+        double d = len_j / (band ? band_len : chunk_len) + (j == 0 ? 1.0 : 0.0) + (jj == n - 1 ? 0.25 : 0.0);
         d = fmin(fmax(d, 0.0), 2.0);
         int bin = (int)((2.0 - d) * 0.5 * classes);
         bin = min(max(bin, 0), classes - 1);

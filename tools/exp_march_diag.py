@@ -7,6 +7,9 @@ import raytracing_jl_b200 as rt
 model, n_azim, delta = rt.synth.workload("cfg3")
 tg = rt.TrackGenerator(rt.Mesh(model), n_azim, delta, bcs=rt.BoundaryConditions(top=rt.Reflective, bottom=rt.Reflective, right=rt.Reflective, left=rt.Reflective))
 rt.trace_(tg)
+for a in sys.argv[1:]:
+    k, v = a.split('=')
+    tg.set_option(k, float(v))
 rt.segmentize_(tg, rtol=1e-6, check=False, fetch_volumes=False)
 st = tg.stats()
 tot = st["knn_queries"]
