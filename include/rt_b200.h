@@ -240,7 +240,7 @@ int rt_debug_chunk_stats(rt_ctx *ctx, double out[8]);
  * mantissas) through the shared-reciprocal division the walk kernels use, compared bit for bit with the IEEE `/`. */
 int rt_selftest_division(rt_ctx *ctx, int64_t n_threads, uint64_t seed, int32_t exp_span, int64_t *mismatches);
 
-/* tuning knobs: "chunk_segments" (minimum expected segments per sub-track chunk, default 192),
+/* tuning knobs: "chunk_segments" (minimum expected segments per sub-track chunk, default 208),
  * "target_walkers" (chunks are sized so that about this many walkers exist, default 148*2048*4),
  * "order_grid" (G: walkers are launched in Morton order of a G x G tiling of the domain, default 32, 0 = uid order),
  * "pipeline" (3: ONE sign-test walk that counts and records every chunk + one lane per segment [default]; 0: sign-test count

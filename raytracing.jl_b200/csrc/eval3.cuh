@@ -33,7 +33,7 @@ constexpr int kEval3Threads = RT_EVAL3_THREADS;
 #define RT_EVAL3_MIN_BLOCKS 32
 #endif
 #ifndef RT_EVAL3_ALIGN
-#define RT_EVAL3_ALIGN 16  // the first lane's output position is a multiple of this many segments (16 doubles = one 128-byte line)
+#define RT_EVAL3_ALIGN 8  // the first lane's output position is a multiple of this many segments (8 doubles = 64 bytes; see below)
 #endif
 #ifndef RT_EVAL3_PF_AHEAD
 #define RT_EVAL3_PF_AHEAD 64  // L2 prefetch distance in units (= 32 warps each); 0: off
@@ -124,11 +124,14 @@ __global__ void __launch_bounds__(kEval3Threads, RT_EVAL3_MIN_BLOCKS) k_eval3(co
     bool bad = false, any_lit = false;
     const int rot = (lane + 31) & 31;
 
-    // The lanes are shifted by sh = (first output position) mod 16 so that every warp store starts on a 128-byte line: lane l of
-    // iteration i evaluates segment v = 32 i + l - sh.  A warp store of 32 x 8 bytes then touches 2 lines and 8 sectors instead
-    // of 3 and 9, and the SM -> L2 path, which the six column streams keep busy for 0.35 of the kernel's 0.9 ms, charges a
-    // request per line and a beat per sector.  The records stay loaded in aligned vectors (one 128-byte line each) and are
-    // rotated into place with two shuffles.
+    // The lanes are shifted by sh = (first output position) mod RT_EVAL3_ALIGN so that every warp store starts on an aligned
+    // boundary of its column: lane l of iteration i evaluates segment v = 32 i + l - sh.  An unaligned warp store of 32 x 8 bytes
+    // touches 3 lines and 9 sectors; aligned to 16 segments (a 128-byte line) it touches 2 lines and 8 sectors, aligned to 8 or 4
+    // segments 3 lines and 8 sectors -- and the SM -> L2 path, which the six column streams keep busy for 0.35 of the kernel's
+    // duration, charges a request per line and a beat per sector (profiles/r2_eval_ablation.txt: -4.9 % for 16).  8 measures
+    // another 1 % faster than 16 (profiles/r2_chunk_band.txt): half as many idle lanes in a chunk's first iteration buy more than
+    // the third line costs.  The records stay loaded in aligned vectors (one 128-byte line each) and are rotated into place with
+    // two shuffles.
     const int sh = (int)(base & (RT_EVAL3_ALIGN - 1));
     const int src_lane = (lane - sh) & 31;
     for (int i0 = 0; i0 < cnt + sh; i0 += 32) {

@@ -130,7 +130,7 @@ struct rt_ctx {
     int opt_band_chunks = 1;           // shorter chunks for tracks that run along the bounding box (walk.cuh k_plan_chunks)
     // ... when that stretch is longer than opt_band_min regular chunks, into chunks opt_band_div times shorter.  Both are relative to
     // the regular chunk: where tracks are plentiful (cfg4, cfg5: a chunk is a whole track) fine chunks would only multiply the
-    // chunk slots.  0.0625 x 192 = 12 crossings: on cfg3 the two angles next to each axis qualify; with the 0.25 of round 1 the
+    // chunk slots.  0.0625 x 208 = 13 crossings: on cfg3 the two angles next to each axis qualify; with the 0.25 of round 1 the
     // second one did not below 128-segment chunks and its band stretches were the walk's longest serial chains
     // (profiles/r2_chunk_band.txt: walk phase 0.70 -> 0.62 ms)
     double opt_band_min = 0.0625;
@@ -151,7 +151,7 @@ struct rt_ctx {
                                        // only.  Three bins: finer ones cost more in locality than they gain in balance (profiles/r2_walk_order.txt)
     int n_sm = 148;
     long long n_units = 0;
-    double opt_chunk_segments = 192.0;              // minimum expected segments per chunk (profiles/r2_chunk_band.txt)
+    double opt_chunk_segments = 208.0;              // minimum expected segments per chunk (profiles/r2_chunk_band.txt)
     double opt_target_walkers = 148.0 * 2048.0 * 4.0;  // chunks are sized so that about this many walkers exist
     double sum_len = 0.0;              // total track length of the shard
     double edge_sum = 0.0, area = 0.0;  // mesh density scalars (chunk sizing)

@@ -86,7 +86,7 @@ struct WalkParams {
     long long zero_vol_n;
 };
 
-constexpr int kRecBlock = 256;  // records per pool block (a multiple of 32): with the default chunks of ~128 segments a walker
+constexpr int kRecBlock = 256;  // records per pool block (a multiple of 32): with the default chunks of at most ~208 segments a walker
                                 // rarely needs a second block, so the claiming atomic stays off the hot path
 
 // smallest sine of a crossing angle the cheap filter of the sign-test walks accepts is 1 / RT_KAPPA_INV ("cheap filter")
@@ -103,7 +103,7 @@ constexpr int kMaxChunksPerTrack = 4096;
 // it walks through boundary-band cells, where every transition is examined exactly on the slow side of the walk kernels (several
 // microseconds instead of one gather).  For the angles closest to the axes that stretch is dozens of cells long at each end (the
 // whole track for the rows next to the boundary): one regular chunk of it is a serial chain that outlasts the rest of the launch.
-// Such a head / tail is therefore cut into 8x shorter chunks:
+// Such a head / tail (longer than band_min regular chunks) is therefore cut into chunks band_div times shorter:
 //     [0, head) in n_head chunks | the middle in n_mid regular chunks | [len - tail, len) in the remaining chunks
 struct ChunkLayout {
     float head, tail;  // lengths of the finely chunked ends (0: none)
@@ -752,19 +752,22 @@ __global__ void k_fixup_tracks(const __grid_constant__ WalkParams P) {
     int total = 0, status = 0;
     double sum = 0.0;
     bool open = true, truncated = false;
+    // (the loads of an iteration do not depend on the running state: requested unconditionally, four iterations at a time)
+#pragma unroll 4
     for (int j = 0; j < n; ++j) {
         long long cidx = c0 + 32LL * j;
-        bool valid = (j == 0) || P.ch.seed_cell[cidx] >= 0;
-        int cnt = (valid && open) ? P.ch.count[cidx] : 0;
+        const int seed_c = P.ch.seed_cell[cidx], cnt_c = P.ch.count[cidx], ec = P.ch.endcode[cidx];
+        const double sum_c = P.ch.sum[cidx];
+        bool valid = (j == 0) || seed_c >= 0;
+        int cnt = (valid && open) ? cnt_c : 0;
         if (valid && open) {
-            int ec = P.ch.endcode[cidx];
             int end = ec & 255, st = ec >> 8;
             if (total + cnt >= P.max_iter) {
                 if (total + cnt > P.max_iter) truncated = true;
                 cnt = P.max_iter - total;
                 open = false;
             }
-            sum += P.ch.sum[cidx];
+            sum += sum_c;
             if (end == END_ERROR) {
                 status = st;
                 open = false;
