@@ -16,8 +16,10 @@
 
 namespace rt {
 
+// one warp per block, like k_eval3: a block's slot is free again the moment its unit is done (64 x 16, 64 x 18 at 56 registers,
+// 128 x 9 measure the same within 0.5 %: profiles/r2_chunk_band.txt r4k; occupancy is not what limits the walk)
 #ifndef RT_MARCH_THREADS
-#define RT_MARCH_THREADS 64
+#define RT_MARCH_THREADS 32
 #endif
 constexpr int kMarchThreads = RT_MARCH_THREADS;
 #ifndef RT_MARCH_WAIT
@@ -25,7 +27,7 @@ constexpr int kMarchThreads = RT_MARCH_THREADS;
 #endif
 constexpr int kMarchWait = RT_MARCH_WAIT;
 #ifndef RT_MARCH_MIN_BLOCKS
-#define RT_MARCH_MIN_BLOCKS 16
+#define RT_MARCH_MIN_BLOCKS 32
 #endif
 
 struct MarchState {
