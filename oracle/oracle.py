@@ -81,6 +81,8 @@ def lib():
         L.orc_seg_counts.argtypes = [vp, C.c_int64, C.c_int64, _i64p, _i32p]
         L.orc_seg_copy.argtypes = [vp, C.c_int64, C.c_int64] + [vp] * 6
         L.orc_seg_stats.argtypes = [vp, _i64p]
+        L.orc_set_diag_ties.argtypes = [C.c_int]
+        L.orc_nn_is_tied.argtypes = [vp, C.c_double, C.c_double]
         L.orc_volumes.argtypes = [vp, _f64p]
         L.orc_seg_free.argtypes = [vp]
         _lib = L
@@ -88,6 +90,14 @@ def lib():
 
 
 RTOL = 1.4901161193847656e-8
+
+
+def set_diag_ties(on: bool):
+    """Count, in ``stats()["nn_ties"]``, the find_element queries whose two nearest nodes are at exactly the same distance -- the only
+    queries whose answer depends on how an exact nearest-neighbour search breaks ties (diagnostic: slows the walk, keep it off
+    in timed runs)."""
+    lib().orc_set_diag_ties(1 if on else 0)
+
 BC = {"Vacuum": 0, "Reflective": 1, "Periodic": 2}
 
 
@@ -234,8 +244,8 @@ class OracleTrackGenerator:
         s = np.zeros(8, np.int64)
         lib().orc_seg_stats(self._h, s)
         names = ["steps", "knn_fallbacks", "k_retries", "same_element_resteps", "boundary_start_steps",
-                 "vertex_steps", "n_int_ge3", "_"]
-        return dict(zip(names[:7], s[:7].tolist()))
+                 "vertex_steps", "n_int_ge3", "nn_ties"]
+        return dict(zip(names, s.tolist()))  # (nn_ties stays 0 unless set_diag_ties(True) was called before segmentize)
 
     def volumes(self):
         v = np.zeros(self.mesh.n_cells)

@@ -219,6 +219,22 @@ int32_t orc_nn(const orc_mesh *m, double x, double y) {
     return s.n ? s.id[0] + 1 : -1;
 }
 
+/* Diagnostic (off by default, never on in a timed run): does the nearest-node query at (x, y) have two nodes at EXACTLY the same
+ * distance?  Only then is the answer of an exact nearest-neighbour search a matter of tie-breaking (lowest node id here and on
+ * the device; NearestNeighbors.jl does not document its choice), i.e. only such queries could make find_element (src/mesh.jl:103-146)
+ * scan the cells of another node first than the reference does. */
+static int g_diag_ties = 0;
+void orc_set_diag_ties(int on) { g_diag_ties = on; }
+
+int orc_nn_is_tied(const orc_mesh *m, double x, double y) {
+    knn_state s;
+    s.k = 2;
+    s.n = 0;
+    s.skip = -1;
+    kd_search(m, 0, x, y, &s);
+    return s.n == 2 && s.d2[0] == s.d2[1];
+}
+
 int orc_knn(const orc_mesh *m, double x, double y, int k, int32_t skip, int32_t *ids) {
     knn_state s;
     if (k > ORC_MAX_K) k = ORC_MAX_K; /* orc_segmentize rejects k > ORC_MAX_K, so this never truncates a walk */
@@ -838,6 +854,7 @@ static int walk_track(const orc_tg *t, int64_t u, orc_segvec *v, int k, double r
         st[0]++;
         int used_knn = 0;
         element = find_element_ex(m, xpx, xpy, 2, &used_knn);
+        if (g_diag_ties) st[7] += orc_nn_is_tied(m, xpx, xpy);
         if (orc_inboundary(m, xpx, xpy, t->tiny_step)) {
             if (v->n == 0) {
                 st[4]++;

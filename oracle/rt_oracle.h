@@ -13,7 +13,8 @@
  *
  * Third-party arithmetic restated from memory of the pinned-by-compat packages (Project.toml:15-23):
  * StaticArrays 1.9 (3x3 closed-form solve, norm), NearestNeighbors 0.4 (exact nn / knn; ties are
- * broken here by lowest node id), Julia Base isapprox.
+ * broken here by lowest node id -- orc_set_diag_ties counts the queries where that matters: none on
+ * the named workloads, profiles/r2_nn_ties.txt), Julia Base isapprox.
  */
 #ifndef RT_ORACLE_H
 #define RT_ORACLE_H
@@ -92,8 +93,11 @@ void orc_seg_counts(const orc_tg *t, int64_t uid_begin, int64_t uid_end, int64_t
 void orc_seg_copy(const orc_tg *t, int64_t uid_begin, int64_t uid_end, double *px, double *py, double *qx,
                   double *qy, double *len, int32_t *element);
 /* walk statistics accumulated by the last orc_segmentize: steps, knn_fallbacks(k=2 branch taken),
- * k_retries, same_element_resteps, boundary_start_steps, vertex_steps, n_int3 */
+ * k_retries, same_element_resteps, boundary_start_steps, vertex_steps, n_int3, nn_ties (only counted after
+ * orc_set_diag_ties(1): find_element queries whose two nearest nodes are at exactly the same distance) */
 void orc_seg_stats(const orc_tg *t, int64_t stats[8]);
+void orc_set_diag_ties(int on);
+int orc_nn_is_tied(const orc_mesh *m, double x, double y); /* the two nearest nodes of (x, y) are at exactly the same distance */
 /* fill_volumes (src/trackgenerator.jl:371-386) over the tracks segmentized so far, uid order */
 void orc_volumes(const orc_tg *t, double *volumes);
 void orc_seg_free(orc_tg *t);

@@ -214,3 +214,36 @@ def test_oracle_on_jittered_mesh():
     for u in range(0, tg.n_total_tracks, 37):
         a, b = off[u], off[u + 1]
         assert np.abs(s["qx"][a:b - 1] - s["px"][a + 1:b]).max(initial=0) < 1e-7
+
+
+def test_nearest_node_ties_never_decide(pincell_model):
+    """The reference locates a point with NearestNeighbors.jl's exact nn / knn (src/mesh.jl:108,124), which does not document how
+    it breaks distance ties; oracle and device take the lowest node id.  That freedom only exists for a query whose two nearest
+    nodes are at EXACTLY the same distance -- and no find_element query of the walks has one: not on the pin cell, the BWR
+    lattice, a jittered mesh, nor on the unjittered structured mesh whose tracks run through vertices (tests/nn_ties.py runs
+    the same count over cfg3 at its named size and over samples of cfg4 / cfg5: 0 in 4.2e8 queries, profiles/r2_nn_ties.txt)."""
+    import raytracing_jl_b200 as rt
+    from oracle import oracle as O
+
+    # the counter sees a tie when there is one: the midpoint of a mesh edge is equidistant from the edge's two nodes
+    sq = rt.Mesh(rt.synth.jittered_triangle_mesh(2, 2, jitter=0.0))
+    om = OracleMesh.from_mesh(sq)
+    x0, y0 = om.xy[0]
+    d2 = ((om.xy - om.xy[0]) ** 2).sum(1)
+    j = int(np.argsort(d2)[1])  # a node nearest to node 0
+    xm, ym = 0.5 * (om.xy[0] + om.xy[j])
+    assert O.lib().orc_nn_is_tied(om._h, float(xm), float(ym)) == 1
+    assert O.lib().orc_nn_is_tied(om._h, float(x0 + 0.25 * (om.xy[j][0] - x0) + 1e-3), float(y0 + 0.25 * (om.xy[j][1] - y0) + 2e-3)) == 0
+
+    cases = [(pincell_model, 8, 2e-2, (1, 1, 1, 1)), (rt.synth.workload("cfg2")[0], 16, 8e-2, (1, 1, 1, 1)),
+             (rt.synth.jittered_triangle_mesh(60, 60, seed=1234), 16, 0.01, (0, 1, 2, 2)),
+             (rt.synth.jittered_triangle_mesh(16, 16, jitter=0.0), 8, 0.0625, (0, 0, 0, 0))]
+    O.set_diag_ties(True)
+    try:
+        for model, n_azim, delta, bcs in cases:
+            tg = OracleTrackGenerator(OracleMesh.from_mesh(rt.Mesh(model)), n_azim, delta, bcs=bcs).trace()
+            tg.segmentize(check=False, fetch=False)
+            st = tg.stats()
+            assert st["steps"] > 2000 and st["nn_ties"] == 0, st
+    finally:
+        O.set_diag_ties(False)
