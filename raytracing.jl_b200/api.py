@@ -425,6 +425,8 @@ class TrackGenerator(TrackLayout):
         return int(sum(a.nbytes for a in self._mesh_arrays()))
 
     def set_option(self, name: str, value: float):
+        """Tuning knob of the library (``rt_set_option``, include/rt_b200.h): "chunk_segments", "band_min", "band_div",
+        "target_walkers", "order_grid", "order_classes", "pipeline", ...  None of them changes a result."""
         _lib.check(self._ctx, _lib.lib().rt_set_option(self._ctx, name.encode(), float(value)))
 
     def timer_start(self):
