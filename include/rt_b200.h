@@ -243,6 +243,8 @@ int rt_selftest_division(rt_ctx *ctx, int64_t n_threads, uint64_t seed, int32_t 
 /* tuning knobs: "chunk_segments" (minimum expected segments per sub-track chunk, default 208),
  * "target_walkers" (chunks are sized so that about this many walkers exist, default 148*2048*4),
  * "order_grid" (G: walkers are launched in Morton order of a G x G tiling of the domain, default 32, 0 = uid order),
+ * "order_classes" (duration bins of the walk's launch order, longest units first, Morton order inside a bin; default 3, 0 = spatial
+ * order only),
  * "pipeline" (3: ONE sign-test walk that counts and records every chunk + one lane per segment [default]; 0: sign-test count
  * walk + geometric fill walk; 1: sequential geometric walks only.  0 and 3 verify themselves and restart in mode 1 on any
  * disagreement; 3 restarts in mode 0 when its record

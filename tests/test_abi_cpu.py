@@ -139,3 +139,17 @@ def test_reference_arm_contract():
     assert d["e2e"] == {"value": d["value"], "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     out = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, timeout=300, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"})
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_every_option_of_rt_set_option_is_documented_in_the_header():
+    """include/rt_b200.h lists the tuning knobs; the list must not drift from what rt_set_option accepts"""
+    import re
+
+    src = open(os.path.join(ROOT, "raytracing.jl_b200", "csrc", "rt_b200.cu")).read()
+    body = src[src.index("int rt_set_option("):]
+    body = body[:body.index("\n}\n")]
+    names = set(re.findall(r'n == "([a-z_0-9]+)"', body))
+    assert len(names) > 10
+    hdr = open(os.path.join(ROOT, "include", "rt_b200.h")).read()
+    missing = sorted(n for n in names if f'"{n}"' not in hdr)
+    assert not missing, missing
