@@ -197,6 +197,32 @@ def test_walk_matches_pure_python(pincell_mesh, pincell_oracle_mesh, n_azim, del
         assert s["element"][off[u]:off[u + 1]].tolist() == [g[5] for g in segs]
 
 
+def test_walk_matches_pure_python_on_other_meshes():
+    """the second, pure-Python restatement (tests/pyref.py: brute-force nearest nodes, barycentric point test, its own walk loop)
+    against the C oracle at segment level on a jittered mesh (knn branch live), the BWR lattice and an unjittered structured mesh"""
+    import raytracing_jl_b200 as rt
+
+    cases = [(rt.synth.jittered_triangle_mesh(20, 20, seed=7), 8, 0.1), (rt.synth.workload("cfg2")[0], 4, 0.9),
+             (rt.synth.jittered_triangle_mesh(12, 12, jitter=0.0), 8, 0.11)]
+    checked = 0
+    for model, n_azim, delta in cases:
+        mesh = rt.Mesh(model)
+        tg = OracleTrackGenerator(OracleMesh.from_mesh(mesh), n_azim, delta).trace()
+        tg.segmentize(check=False)
+        ref = pyref.PyRef(mesh)
+        t, s, off = tg.tracks, tg.seg, tg.seg_offsets
+        for u in range(tg.n_total_tracks):
+            if tg.seg_status[u] != 0:
+                continue
+            segs = ref.walk(tuple(t["p"][u]), float(t["phi"][u]), tuple(t["abc"][u]))
+            assert len(segs) == off[u + 1] - off[u], (u, len(segs))
+            got = np.stack([s[k][off[u]:off[u + 1]] for k in ("px", "py", "qx", "qy", "len")], 1)
+            assert np.array_equal(got, np.array([g[:5] for g in segs]).reshape(-1, 5))
+            assert s["element"][off[u]:off[u + 1]].tolist() == [g[5] for g in segs]
+            checked += len(segs)
+    assert checked > 1500
+
+
 def test_oracle_on_jittered_mesh():
     """on jittered meshes the knn branch of find_element is live; no errors expected."""
     import raytracing_jl_b200 as rt
