@@ -56,8 +56,17 @@ class PyRef:
     def node_cells(self, n):
         return self.nd[self.np_[n - 1] - 1:self.np_[n] - 1]
 
-    def pit(self, c, x):
+    def pie(self, c, x):
+        """point_in_element dispatched on the number of nodes (the reference's TODO at src/mesh.jl:148): a quadrilateral is tested
+        with the four triangles (k1, k2, k3), k_j = mod1(i + j - 1, 4), of point_in_quadrangle (src/mesh.jl:184-201)"""
         n = self.cell_nodes(c)
+        if len(n) == 4:
+            return any(self.pit(c, x, [n[(i + j) % 4] for j in range(3)]) for i in range(4))
+        return self.pit(c, x)
+
+    def pit(self, c, x, n=None):
+        if n is None:
+            n = self.cell_nodes(c)
         (x1, y1), (x2, y2), (x3, y3) = (self.xy[n[0] - 1], self.xy[n[1] - 1], self.xy[n[2] - 1])
         x1, y1, x2, y2, x3, y3 = map(float, (x1, y1, x2, y2, x3, y3))
         d = x1 * (y2 - y3) + y1 * (x3 - x2) + (x2 * y3 - y2 * x3)
@@ -76,7 +85,7 @@ class PyRef:
         ids = self.nearest(x, k + 1)
         for nid in ids:
             for c in self.node_cells(nid):
-                if self.pit(c, x):
+                if self.pie(c, x):
                     return int(c)
         return -1
 

@@ -199,11 +199,14 @@ def test_walk_matches_pure_python(pincell_mesh, pincell_oracle_mesh, n_azim, del
 
 def test_walk_matches_pure_python_on_other_meshes():
     """the second, pure-Python restatement (tests/pyref.py: brute-force nearest nodes, barycentric point test, its own walk loop)
-    against the C oracle at segment level on a jittered mesh (knn branch live), the BWR lattice and an unjittered structured mesh"""
+    against the C oracle at segment level on a jittered mesh (knn branch live), the BWR lattice, an unjittered structured mesh and
+    two meshes with quadrilaterals"""
     import raytracing_jl_b200 as rt
 
     cases = [(rt.synth.jittered_triangle_mesh(20, 20, seed=7), 8, 0.1), (rt.synth.workload("cfg2")[0], 4, 0.9),
-             (rt.synth.jittered_triangle_mesh(12, 12, jitter=0.0), 8, 0.11)]
+             (rt.synth.jittered_triangle_mesh(12, 12, jitter=0.0), 8, 0.11),
+             (rt.synth.mixed_quad_triangle_mesh(14, 14, seed=3), 8, 0.09),  # quadrilaterals: point_in_quadrangle, 4-edge intersections
+             (rt.synth.mixed_quad_triangle_mesh(10, 12, quad_fraction=1.0, seed=5), 4, 0.3)]
     checked = 0
     for model, n_azim, delta in cases:
         mesh = rt.Mesh(model)
@@ -220,7 +223,7 @@ def test_walk_matches_pure_python_on_other_meshes():
             assert np.array_equal(got, np.array([g[:5] for g in segs]).reshape(-1, 5))
             assert s["element"][off[u]:off[u + 1]].tolist() == [g[5] for g in segs]
             checked += len(segs)
-    assert checked > 1500
+    assert checked > 2500
 
 
 def test_oracle_on_jittered_mesh():
