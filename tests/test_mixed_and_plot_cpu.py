@@ -1,6 +1,8 @@
 """SURVEY 8(f)-4 on the CPU: the oracle's restatement of point_in_quadrangle (src/mesh.jl:184-201) and of the 4-edge
 intersections (src/intersection.jl:42-44, 81-95) on quadrilateral cells, mixed-mesh host tables, and the plot-friendly views of
 src/plot_recipes.jl."""
+import os
+
 import numpy as np
 import pytest
 
@@ -82,3 +84,15 @@ def test_plot_views_match_the_recipes():
     assert np.array_equal(sx, [[0, 1], [1, 2]]) and np.array_equal(sz, [[7, 9], [7, 9]])
     fx, fy, fz = rt.plotdata.flat_polyline(sx, sy, sz)
     assert np.array_equal(fx[[0, 1, 3, 4]], [0, 1, 1, 2]) and np.isnan(fx[2]) and fx.size == 5 and np.array_equal(fz[[0, 1, 3, 4]], [7, 7, 9, 9])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/demo"), reason="the reference tree only exists in the build container")
+def test_mesh_readers_on_the_reference_files():
+    """Both mesh files the reference ships for its quick start (demo/pincell.json: Gridap JSON, loaded by test/runtests.jl:5-6;
+    demo/pincell.msh: MSH 4.1) read into the same model, which is the committed fixture tests/golden/pincell.npz."""
+    import raytracing_jl_b200 as rt
+
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pincell.npz"))
+    for m in (rt.DiscreteModelFromFile("/root/reference/demo/pincell.json"), rt.GmshDiscreteModel("/root/reference/demo/pincell.msh")):
+        assert np.array_equal(m.node_coordinates, d["node_coordinates"])
+        assert np.array_equal(m.cell_ptrs, d["cell_ptrs"]) and np.array_equal(m.cell_data, d["cell_data"])
