@@ -1,4 +1,4 @@
-"""GPU experiment: the single-walk pipeline (3) against the hybrid (0) and two-stage (2) ones; chunk size / order sweeps."""
+"""GPU experiment: the single-walk pipeline (3) against the hybrid one (0), k_march against k_topo<2>; chunk size / order sweeps."""
 import os
 import sys
 
