@@ -153,3 +153,64 @@ def test_every_option_of_rt_set_option_is_documented_in_the_header():
     hdr = open(os.path.join(ROOT, "include", "rt_b200.h")).read()
     missing = sorted(n for n in names if f'"{n}"' not in hdr)
     assert not missing, missing
+
+
+def _c_prototypes():
+    """{name: [kind of every parameter]} from include/rt_b200.h; kinds: ptr, i32, i64, f64"""
+    import re
+
+    hdr = open(os.path.join(ROOT, "include", "rt_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|void|const char \*)\s*(rt_[a-z_0-9]+)\s*\(([^;{}]*?)\)\s*;", hdr, flags=re.S):
+        name, args = m.group(1), " ".join(m.group(2).split())
+        kinds = []
+        for a in ([] if args in ("", "void") else args.split(",")):
+            a = a.strip()
+            if "*" in a or "[" in a or a.startswith("rt_batch_cb"):
+                kinds.append("ptr")
+            elif re.match(r"(const )?(int32_t|uint32_t|int|unsigned)\b", a):
+                kinds.append("i32")
+            elif re.match(r"(const )?(int64_t|uint64_t|long long|size_t)\b", a):
+                kinds.append("i64")
+            elif re.match(r"(const )?double\b", a):
+                kinds.append("f64")
+            else:
+                raise AssertionError(f"unparsed parameter {a!r} of {name}")
+        protos[name] = kinds
+    return protos
+
+
+def test_julia_glue_calls_match_the_header():
+    """julia/RayTracingB200.jl cannot run here (no Julia in the image): at least every `ccall` in it must name an exported
+    function and pass the same number of arguments, of the same machine kind (pointer / 32-bit / 64-bit integer / double) and in
+    the same order, as the prototype in include/rt_b200.h."""
+    import re
+
+    protos = _c_prototypes()
+    assert len(protos) >= 30 and protos["rt_create"] == ["ptr", "i32"]
+    src = open(os.path.join(ROOT, "julia", "RayTracingB200.jl")).read()
+    kind = {"Int32": "i32", "Cint": "i32", "UInt32": "i32", "Int64": "i64", "UInt64": "i64", "Csize_t": "i64", "Float64": "f64",
+            "Cdouble": "f64", "Cstring": "ptr"}
+    calls = list(re.finditer(r"ccall\(\(:(rt_[a-z_0-9]+),\s*LIBRT_B200\),\s*(\w+),\s*\(", src))
+    assert len(calls) >= 15
+    for m in calls:
+        name, ret = m.group(1), m.group(2)
+        assert name in protos, name
+        i, depth, start = m.end(), 1, m.end()
+        while depth:  # the argument-type tuple ends at the matching parenthesis
+            depth += {"(": 1, ")": -1}.get(src[i], 0)
+            i += 1
+        types, cur, d = [], "", 0
+        for ch in src[start:i - 1]:
+            if ch == "," and d == 0:
+                types.append(cur.strip())
+                cur = ""
+            else:
+                d += {"{": 1, "}": -1}.get(ch, 0)
+                cur += ch
+        if cur.strip():
+            types.append(cur.strip())
+        got = ["ptr" if t.startswith("Ptr{") else kind[t] for t in types]
+        assert got == protos[name], (name, got, protos[name])
+        assert ret in ("Cint", "Cvoid", "Cstring")
