@@ -214,3 +214,26 @@ def test_julia_glue_calls_match_the_header():
         got = ["ptr" if t.startswith("Ptr{") else kind[t] for t in types]
         assert got == protos[name], (name, got, protos[name])
         assert ret in ("Cint", "Cvoid", "Cstring")
+
+
+def test_ctypes_table_matches_the_header():
+    """raytracing.jl_b200/_lib.py SYMBOLS against include/rt_b200.h: same functions, same number, order and machine kind of
+    arguments (a wrong width in a ctypes prototype corrupts a call silently)"""
+    import ctypes as C
+
+    from raytracing_jl_b200 import _lib
+
+    protos = _c_prototypes()
+    assert set(_lib.SYMBOLS) == set(protos), set(_lib.SYMBOLS) ^ set(protos)
+
+    def kind(t):
+        if t in (C.c_int, C.c_int32, C.c_uint32):
+            return "i32"
+        if t in (C.c_int64, C.c_uint64, C.c_size_t, C.c_longlong):
+            return "i64"
+        if t is C.c_double:
+            return "f64"
+        return "ptr"  # c_void_p, c_char_p, POINTER(...), ndpointer, CFUNCTYPE
+
+    for name, (_, args) in _lib.SYMBOLS.items():
+        assert [kind(t) for t in args] == protos[name], (name, [kind(t) for t in args], protos[name])
